@@ -1,0 +1,326 @@
+"""CPU fp32 oracle for the SRGAN training-step hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, never the product: only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The product package
+(``single-image-super-resolution_b200``) must never route through it.
+
+It is an independent *functional* restatement of the reference's algorithm: every network is a
+pure function of a ``state`` dict that uses the reference's ``state_dict`` key names, so the same
+tensors can be fed to the reference modules, to this oracle and to the CUDA path.  All arithmetic
+is plain PyTorch fp32 on the CPU (the reference's own arithmetic type).
+
+Parity pin: ``oracle/validate_against_reference.py`` runs the real reference modules and the
+unmodified ``train.train_loop`` from ``/root/reference`` against these functions (outputs, every
+parameter gradient, the post-step weights) and writes the golden vectors in ``tests/golden``.
+The reference itself ships no golden vectors or numerical tests.
+
+Reference citations (file:line in /root/reference):
+  model_generator.py:5-19 (BasicBlock), 23-63 (Generator), 86-101 (forward), 117-141 (suffix)
+  model_discriminator.py:5-15, 18-62
+  model_content_extractor.py:6-7, 33-60
+  train.py:33-122 (step), 128-168 (D loss), 171-181 (G adversarial loss), 183-186 (content loss)
+  config.py:141,156-159 (loss weights), 186-188 (labels), 293-294 (Adam)
+Third-party algorithms restated (PyTorch is an un-pinned dependency of the reference; the
+de-facto pin is torch 2.11.0): legacy ``torch.nn.utils.spectral_norm`` (one power iteration per
+training forward, sigma = u^T W v, gradient through sigma with u, v constant), ``BatchNorm2d``
+train mode (biased batch variance for normalisation, unbiased for the running estimate,
+momentum 0.1, eps 1e-5), ``BCELoss`` (log clamped at -100), ``Adam`` (bias-corrected, eps 1e-8).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+State = Dict[str, torch.Tensor]
+
+LEAKY_SLOPE = 0.01  # nn.LeakyReLU() default, model_discriminator.py:12,40,50
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+SN_EPS = 1e-12
+
+# torchvision VGG19 "features" layout (configuration E): index -> out channels for convs.
+VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M",
+             512, 512, 512, 512, "M"]
+# 1-based positions of the conv that precedes each max-pool, model_content_extractor.py:6-7
+VGG_TAPS_1BASED = (3, 8, 17, 26, 35)
+
+
+def vgg19_feature_layers() -> List[Tuple[str, int, int]]:
+    """[(kind, cin, cout)] for torchvision's vgg19().features, kind in conv/relu/pool."""
+    layers, cin = [], 3
+    for v in VGG19_CFG:
+        if v == "M":
+            layers.append(("pool", cin, cin))
+        else:
+            layers.append(("conv", cin, v))
+            layers.append(("relu", v, v))
+            cin = v
+    return layers
+
+
+# --------------------------------------------------------------------------- primitives
+def sn_weight(st: State, p: str, training: bool) -> torch.Tensor:
+    """Legacy spectral norm: returns W_orig / sigma and (training) updates u, v in place."""
+    w = st[p + "weight_orig"]
+    u, v = st[p + "weight_u"], st[p + "weight_v"]
+    wm = w.reshape(w.shape[0], -1)
+    if training:
+        with torch.no_grad():
+            t = torch.mv(wm.t(), u)
+            v.copy_(t / t.norm().clamp_min(SN_EPS))
+            s = torch.mv(wm, v)
+            u.copy_(s / s.norm().clamp_min(SN_EPS))
+        u, v = u.clone(), v.clone()
+    sigma = torch.dot(u, torch.mv(wm, v))
+    return w / sigma
+
+
+def conv(st: State, p: str, x: torch.Tensor, stride: int, pad: int, training: bool) -> torch.Tensor:
+    w = sn_weight(st, p, training) if (p + "weight_orig") in st else st[p + "weight"]
+    return F.conv2d(x, w, st[p + "bias"], stride=stride, padding=pad)
+
+
+def batch_norm(st: State, p: str, x: torch.Tensor, training: bool) -> torch.Tensor:
+    g, b = st[p + "weight"], st[p + "bias"]
+    rm, rv = st[p + "running_mean"], st[p + "running_var"]
+    if not training:
+        scale = g / torch.sqrt(rv + BN_EPS)
+        return x * scale[None, :, None, None] + (b - rm * scale)[None, :, None, None]
+    n = x.numel() // x.shape[1]
+    mean = x.mean(dim=(0, 2, 3))
+    var = x.var(dim=(0, 2, 3), unbiased=False)
+    with torch.no_grad():
+        rm.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean)
+        rv.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var * (n / max(n - 1, 1)))
+        if (p + "num_batches_tracked") in st:
+            st[p + "num_batches_tracked"] += 1
+    xhat = (x - mean[None, :, None, None]) / torch.sqrt(var + BN_EPS)[None, :, None, None]
+    return xhat * g[None, :, None, None] + b[None, :, None, None]
+
+
+def prelu(st: State, p: str, x: torch.Tensor) -> torch.Tensor:
+    a = st[p + "weight"]
+    return torch.clamp_min(x, 0) + a * torch.clamp_max(x, 0)
+
+
+def leaky(x: torch.Tensor) -> torch.Tensor:
+    return torch.clamp_min(x, 0) + LEAKY_SLOPE * torch.clamp_max(x, 0)
+
+
+def pixel_shuffle(x: torch.Tensor, r: int) -> torch.Tensor:
+    b, c, h, w = x.shape
+    x = x.reshape(b, c // (r * r), r, r, h, w)
+    return x.permute(0, 1, 4, 2, 5, 3).reshape(b, c // (r * r), h * r, w * r)
+
+
+def bce(p: torch.Tensor, target: float) -> torch.Tensor:
+    """nn.BCELoss(reduction='mean') against a constant target, log clamped at -100."""
+    logp = torch.log(p).clamp_min(-100.0)
+    log1mp = torch.log(1 - p).clamp_min(-100.0)
+    return -(target * logp + (1 - target) * log1mp).mean()
+
+
+# --------------------------------------------------------------------------- generator
+def _count(st: State, fmt: str) -> int:
+    n = 0
+    while fmt.format(n) in st:
+        n += 1
+    return n
+
+
+def generator_forward_no_end(st: State, x: torch.Tensor, p: str = "", training: bool = True,
+                             scales: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """model_generator.py:86-96 (Generator) / 133-136 (GeneratorSuffix), selected by key layout."""
+    if any(k.startswith(p + "base.") for k in st):
+        x = generator_forward_no_end(st, x, p + "base.", training, scales)
+        x = conv(st, p + "upscale.0.", x, 1, 1, training)
+        x = pixel_shuffle(x, 2)
+        return prelu(st, p + "upscale.2.", x)
+    x = conv(st, p + "first_layers.0.", x, 1, 4, training)
+    x = prelu(st, p + "first_layers.1.", x)
+    skip = x
+    n_blocks = _count(st, p + "block_list.{}.layers.0.bias")
+    for i in range(n_blocks):
+        q = f"{p}block_list.{i}.layers."
+        y = conv(st, q + "0.", x, 1, 1, training)
+        y = batch_norm(st, q + "1.", y, training)
+        y = prelu(st, q + "2.", y)
+        y = conv(st, q + "3.", y, 1, 1, training)
+        y = batch_norm(st, q + "4.", y, training)
+        x = x + y
+    x = conv(st, p + "block_list_end.0.", x, 1, 1, training)
+    x = batch_norm(st, p + "block_list_end.1.", x, training)
+    x = x + skip
+    n_up = _count(st, p + "upscale.{}.0.bias")
+    for s in range(n_up):
+        q = f"{p}upscale.{s}."
+        x = conv(st, q + "0.", x, 1, 1, training)
+        x = pixel_shuffle(x, scales[s] if scales else 2)
+        x = prelu(st, q + "2.", x)
+    return x
+
+
+def _end_prefix(st: State, p: str = "") -> str:
+    while any(k.startswith(p + "base.") for k in st):
+        p += "base."
+    return p + "end.0."
+
+
+def generator_forward(st: State, x: torch.Tensor, training: bool = True,
+                      scales: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """model_generator.py:98-101 / 138-141: trunk + upscale stages, then the shared end conv + tanh."""
+    x = generator_forward_no_end(st, x, "", training, scales)
+    return torch.tanh(conv(st, _end_prefix(st), x, 1, 1, training))
+
+
+# --------------------------------------------------------------------------- discriminator
+def discriminator_forward(st: State, x: torch.Tensor, strides: Sequence[int],
+                          training: bool = True) -> torch.Tensor:
+    """model_discriminator.py:55-62.  Output shape (B, 1), post-sigmoid."""
+    b = x.shape[0]
+    x = leaky(conv(st, "conv.0.", x, strides[0], 1, training))
+    for k in range(len(strides) - 1):
+        q = f"conv.2.{k}.layers."
+        x = conv(st, q + "0.", x, strides[k + 1], 1, training)
+        x = leaky(batch_norm(st, q + "1.", x, training))
+    x = x.reshape(b, -1)  # NCHW (c, h, w) order
+    x = leaky(F.linear(x, st["fc.0.weight"], st["fc.0.bias"]))
+    x = F.linear(x, st["fc.2.weight"], st["fc.2.bias"])
+    return torch.sigmoid(x)
+
+
+# --------------------------------------------------------------------------- VGG extractor
+def vgg_kept_positions(mask: int) -> List[int]:
+    return [VGG_TAPS_1BASED[i] for i in range(5) if mask & (1 << i)]
+
+
+def masked_vgg_forward(st: State, x: torch.Tensor, mask: int) -> torch.Tensor:
+    """model_content_extractor.py:51-60 including the in-place-ReLU quirk: every tap except the
+    last is observed *after* the following ReLU (torchvision uses ReLU(inplace=True) and the
+    reference keeps a reference to the conv output), the last tap is the raw conv output."""
+    kept = vgg_kept_positions(mask)
+    layers = vgg19_feature_layers()[: kept[-1]]
+    taps = []
+    for i, (kind, _, _) in enumerate(layers, 1):
+        if kind == "conv":
+            x = F.conv2d(x, st[f"layers.{i - 1}.weight"], st[f"layers.{i - 1}.bias"], padding=1)
+            if i in kept and i == kept[-1]:
+                taps.append(x)
+        elif kind == "relu":
+            x = torch.relu(x)
+            if (i - 1) in kept:
+                taps.append(x)
+        else:
+            x = F.max_pool2d(x, 2, 2)
+    return torch.cat([t.reshape(t.shape[0], -1) for t in taps], dim=1)
+
+
+# --------------------------------------------------------------------------- optimiser
+class AdamState:
+    """torch.optim.Adam(lr, betas=(.9,.999), eps=1e-8, weight_decay=0) restated (config.py:293-294)."""
+
+    def __init__(self, names: Sequence[str], lr: float, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.names, self.lr, self.betas, self.eps = list(names), lr, betas, eps
+        self.step_count = 0
+        self.m: Dict[str, torch.Tensor] = {}
+        self.v: Dict[str, torch.Tensor] = {}
+
+    @torch.no_grad()
+    def step(self, st: State, grads: Dict[str, Optional[torch.Tensor]], lr_scale: float = 1.0):
+        self.step_count += 1
+        b1, b2 = self.betas
+        bc1 = 1 - b1 ** self.step_count
+        bc2 = 1 - b2 ** self.step_count
+        for k in self.names:
+            g = grads.get(k)
+            if g is None:
+                continue
+            if k not in self.m:
+                self.m[k] = torch.zeros_like(st[k])
+                self.v[k] = torch.zeros_like(st[k])
+            self.m[k].mul_(b1).add_(g, alpha=1 - b1)
+            self.v[k].mul_(b2).addcmul_(g, g, value=1 - b2)
+            denom = (self.v[k].sqrt() / math.sqrt(bc2)).add_(self.eps)
+            st[k].addcdiv_(self.m[k], denom, value=-(self.lr * lr_scale) / bc1)
+
+
+# --------------------------------------------------------------------------- training step
+def trainable_names(st: State) -> List[str]:
+    skip = ("weight_u", "weight_v", "running_mean", "running_var", "num_batches_tracked")
+    return [k for k in st if not k.endswith(skip)]
+
+
+def _leaf(st: State, names: Sequence[str]) -> State:
+    out = dict(st)
+    for k in names:
+        out[k] = st[k].detach().requires_grad_(True)
+    return out
+
+
+def train_step(g: State, d: State, vgg: State, hr: torch.Tensor, lr_img: torch.Tensor, *,
+               d_strides: Sequence[int], vgg_mask: int, opt_g: AdamState, opt_d: AdamState,
+               w_adv_g: float = 5e-2, w_adv_d: float = 1.0, w_cont: float = 1.0,
+               real_label: float = 1.0, real_label_reduced: float = 0.9, fake_label: float = 0.0,
+               g_trainable: Optional[Sequence[str]] = None, old_fakes: Sequence[torch.Tensor] = (),
+               lr_scale: float = 1.0) -> Dict[str, object]:
+    """One iteration of train.py:33-122 (supervised mode, replay list passed explicitly).
+
+    ``g``/``d`` are updated in place (weights, SN u/v, BN running stats) exactly as the reference
+    modules would be.  Returns losses, the fake batch and the gradients that the optimisers saw.
+    """
+    g_names = list(g_trainable) if g_trainable is not None else trainable_names(g)
+    d_names = trainable_names(d)
+    gl = _leaf(g, g_names)
+    fake = generator_forward(gl, lr_img, training=True)              # train.py:53
+
+    # ---- D update, train.py:56-75 and 128-168
+    dl = _leaf(d, d_names)
+    d_real = discriminator_forward(dl, hr, d_strides, True).view(-1)
+    err_d = bce(d_real, real_label_reduced)
+    d_fake_mean = 0.0
+    for fk in [fake.detach(), *old_fakes]:
+        d_fake = discriminator_forward(dl, fk, d_strides, True).view(-1)
+        err_d = err_d + bce(d_fake, fake_label)
+        d_fake_mean += float(d_fake.mean())
+    err_d = err_d * w_adv_d
+    d_grads = dict(zip(d_names, torch.autograd.grad(err_d, [dl[k] for k in d_names])))
+    for k in ("weight_u", "weight_v", "running_mean", "running_var", "num_batches_tracked"):
+        pass  # buffers were updated in place through the shared tensors of ``d``
+    opt_d.step(d, d_grads, lr_scale)
+
+    # ---- G update, train.py:81-108, 171-186
+    dl2 = _leaf(d, d_names)
+    out = discriminator_forward(dl2, fake, d_strides, True).view(-1)
+    err_g_adv = bce(out, real_label) * w_adv_g
+    feat_real = masked_vgg_forward(vgg, hr, vgg_mask)
+    feat_fake = masked_vgg_forward(vgg, fake, vgg_mask)
+    err_g_cont = torch.mean((feat_real - feat_fake) ** 2) * w_cont
+    err_g = err_g_adv + err_g_cont
+    g_grads = dict(zip(g_names, torch.autograd.grad(err_g, [gl[k] for k in g_names],
+                                                    allow_unused=True)))
+    opt_g.step(g, g_grads, lr_scale)
+    return {
+        "fake": fake.detach(), "err_d": float(err_d), "err_g_adv": float(err_g_adv),
+        "err_g_cont": float(err_g_cont), "d_x": float(d_real.mean()), "d_g_z1": d_fake_mean,
+        "d_g_z2": float(out.mean()), "d_grads": d_grads, "g_grads": g_grads,
+    }
+
+
+# --------------------------------------------------------------------------- LR synthesis
+def lr_from_hr(hr: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """utils.py:16-31: bicubic (align_corners=True, A=-0.75) down-sampling, clamped to [-1, 1]."""
+    return F.interpolate(hr, size, mode="bicubic", align_corners=True).clamp(-1.0, 1.0)
+
+
+# --------------------------------------------------------------------------- metrics
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 2.0) -> float:
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)

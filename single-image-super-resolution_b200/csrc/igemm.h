@@ -1,0 +1,58 @@
+// Internal C++ interface of the tcgen05 implicit-GEMM engine (not part of the C ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sisr {
+
+constexpr int kMaxTaps = 9;
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_PRELU = 3, ACT_TANH = 4 };
+
+// One "tap" = one (dy, dx) filter position: the im2col offset added to the traversal position
+// and the first weight-matrix column holding that tap's Cin channels.
+struct IgemmTaps {
+  uint16_t off_w[kMaxTaps];
+  uint16_t off_h[kMaxTaps];
+  int32_t k_off[kMaxTaps];
+};
+
+// D[M, Cout] = sum_taps A_tap[M, Cin] * Wt[Cout, k_off(tap) .. +Cin]^T
+//   rows of A are the NB*GH*GW positions of a traversal grid over an NHWC bf16 tensor:
+//   position (n, gh, gw) reads input pixel (gh*trav_stride + lower_h + off_h,
+//                                           gw*trav_stride + lower_w + off_w), zero outside.
+struct IgemmProblem {
+  // input activation tensor
+  const __nv_bfloat16* x;
+  int NB, H, W, Cin;
+  // traversal grid / bounding box
+  int GH, GW;
+  int trav_stride;
+  int lower_w, lower_h, upper_w, upper_h;
+  // weights [Cout, Ktot] row-major bf16 (K contiguous)
+  const __nv_bfloat16* w;
+  int Cout, Ktot;
+  int num_taps;
+  IgemmTaps taps;
+  // output: row (n, gh, gw), column c ->
+  //   out[((n*OH + gh*osy + opy)*OW + gw*osx + opx)*ldc + c]          (ps_c == 0)
+  //   out[((n*OH + gh*2 + i)*OW + gw*2 + j)*ldc + (c % ps_c)], (i,j) = divmod(c / ps_c, 2)  (ps_c > 0)
+  __nv_bfloat16* out;
+  int OH, OW, ldc;
+  int osy, osx, opy, opx;
+  int ps_c;
+  // fused epilogue
+  const float* bias;       // [Cout] or nullptr (indexed by GEMM column)
+  int act;                 // Act
+  float slope;             // ACT_LEAKY
+  const float* slope_ptr;  // ACT_PRELU (single learnable slope)
+  float* stats;            // [2*Cout] += {sum, sum of squares} of the stored bf16 values, or nullptr
+};
+
+// Returns 0 on success; message via igemm_last_error().
+int igemm_launch(const IgemmProblem& p, cudaStream_t stream);
+bool igemm_supported(const IgemmProblem& p);
+const char* igemm_last_error();
+
+}  // namespace sisr
