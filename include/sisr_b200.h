@@ -1,0 +1,146 @@
+/* sisr_b200 -- C ABI of the B200-native SRGAN training-step kernels.
+ *
+ * The reference (keyber/Single-Image-Super-Resolution) is pure Python: it has no FFI / plugin
+ * interface of its own, every operator on its hot path is an ATen library call made from
+ * nn.Module.forward.  This header is therefore the boundary a maintainer
+ * would bind in place of those ATen calls; each entry cites the reference call site it replaces.
+ * The reference-side binding (a ctypes stub) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - activations are NHWC bf16 (uint16_t storage), parameters / gradients / statistics fp32;
+ *   - no allocation, no ownership: outputs and workspaces are caller-provided;
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*); CUDA-graph capturable;
+ *   - return 0 on success, non-zero on error, message via sisr_last_error() (thread-local).
+ */
+#ifndef SISR_B200_H_
+#define SISR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t sisr_bf16;
+
+/* activation codes for fused epilogues */
+enum { SISR_ACT_NONE = 0, SISR_ACT_RELU = 1, SISR_ACT_LEAKY = 2, SISR_ACT_PRELU = 3, SISR_ACT_TANH = 4 };
+
+/* Convolution geometry: input [n,h,w,cin] -> output [n,oh,ow,cout], square kernel/stride/pad.
+ * ps_r = 2 means the conv is followed by PixelShuffle(2): the output is written directly as
+ * [n, 2*oh, 2*ow, cout/4] and the prepared weights carry the matching row permutation. */
+typedef struct sisr_conv_desc {
+  int n, h, w, cin;
+  int oh, ow, cout;
+  int k, stride, pad;
+  int ps_r;
+} sisr_conv_desc;
+
+const char* sisr_last_error(void);
+int sisr_abi_version(void);
+/* 1 if the tcgen05 implicit-GEMM engine takes this fprop/dgrad shape, 0 if the CUDA-core kernel does */
+int sisr_conv_uses_tensor_cores(const sisr_conv_desc* d);
+
+/* ---- layout at the module boundary (NCHW fp32 <-> NHWC bf16); replaces nothing in the reference,
+ *      it is the price of keeping the reference's NCHW fp32 tensors at the nn.Module surface ---- */
+int sisr_nchw_f32_to_nhwc_bf16(const float* x, sisr_bf16* y, int n, int c, int h, int w, void* stream);
+int sisr_nhwc_bf16_to_nchw_f32(const sisr_bf16* x, float* y, int n, int c, int h, int w, void* stream);
+/* x: [batch][rows][cols] -> y: [batch][cols][rows]  (discriminator flatten, model_discriminator.py:59) */
+int sisr_transpose_bf16(const sisr_bf16* x, sisr_bf16* y, int batch, int rows, int cols, void* stream);
+/* dpre[nhwc bf16] = dout[nchw f32] * (1 - y[nchw f32]^2)   (Tanh backward, model_generator.py:53,63) */
+int sisr_tanh_bwd_nchw_to_nhwc(const float* dout, const float* y, sisr_bf16* dpre, int n, int c, int h,
+                               int w, void* stream);
+
+/* ---- spectral norm + weight preparation: torch.nn.utils.spectral_norm as applied at
+ *      model_generator.py:10,13,33,39,45,52,123 and model_discriminator.py:10,39 ---- */
+size_t sisr_sn_workspace_floats(int cout, int k);
+int sisr_sn_power_iteration(const float* w_orig, float* u, float* v, float* sigma, int cout, int k,
+                            int training, float eps, float* workspace, void* stream);
+/* w: [cout,cin,k,k] fp32 -> w_fprop: [cout',k,k,cin] bf16, w_dgrad: [cin,k,k,cout'] bf16 (nullable),
+ * both scaled by 1/sigma (sigma nullable); bias_perm (nullable) = bias in the permuted row order. */
+int sisr_weight_prep(const float* w, const float* sigma, const float* bias, sisr_bf16* w_fprop,
+                     sisr_bf16* w_dgrad, float* bias_perm, int cout, int cin, int k, int ps_r,
+                     void* stream);
+/* g_prepared: fp32 [cout',k,k,cin] from sisr_conv_wgrad -> dw: [cout,cin,k,k] fp32 including the
+ * gradient through sigma (u, v constant); sigma == NULL means no spectral norm. workspace: 4 floats */
+int sisr_weight_grad_finish(const float* g_prepared, const float* w_orig, const float* u, const float* v,
+                            const float* sigma, float* dw, const float* dbias_perm, float* dbias,
+                            int cout, int cin, int k, int ps_r, int accumulate, float* workspace,
+                            void* stream);
+
+/* ---- convolutions: nn.Conv2d at model_generator.py:10,13,33,39,45,52,123,
+ *      model_discriminator.py:10,39 and torchvision vgg19.features (model_content_extractor.py:43) ---- */
+/* y (bf16 NHWC, or pixel-shuffled) and/or y_nchw_f32 (fp32 NCHW, edge layers only) = act(conv(x)+bias).
+ * stats (nullable): fp32 [2*cout] overwritten with per-channel {sum, sum of squares} of y (BN batch
+ * statistics, fused in the conv epilogue on the tensor-core path). */
+int sisr_conv_fprop(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16* w_fprop,
+                    const float* bias, int act, float slope, const float* slope_ptr, sisr_bf16* y,
+                    float* y_nchw_f32, float* stats, void* stream);
+/* dx = conv_transpose(dy): dy is the gradient w.r.t. the pre-activation conv output in the layout
+ * fprop wrote it (pixel-shuffled when ps_r = 2). */
+int sisr_conv_dgrad(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf16* w_fprop,
+                    const sisr_bf16* w_dgrad, sisr_bf16* dx, void* stream);
+/* g_prepared: fp32 [cout',k,k,cin] (overwritten); dbias_perm: fp32 [cout'] nullable.
+ * workspace: sisr_conv_wgrad_workspace_bytes(d) bytes (split-K partials), may be NULL if that is 0. */
+size_t sisr_conv_wgrad_workspace_bytes(const sisr_conv_desc* d);
+int sisr_conv_wgrad(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16* dy, float* g_prepared,
+                    float* dbias_perm, void* workspace, void* stream);
+
+/* ---- BatchNorm2d (train / eval) fused with PReLU / LeakyReLU / residual add:
+ *      model_generator.py:11-14,16-19,40,93 and model_discriminator.py:11-12 ---- */
+int sisr_bn_stats(const sisr_bf16* y, long long rows, int c, float* stats, void* stream);
+int sisr_bn_finalize(const float* stats, float count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, long long* num_batches_tracked,
+                     float momentum, float eps, int training, float* scale, float* shift, float* mean,
+                     float* invstd, int c, void* stream);
+int sisr_bn_apply(const sisr_bf16* y, const float* scale, const float* shift, int act, float slope,
+                  const float* slope_ptr, const sisr_bf16* residual, sisr_bf16* out, long long rows,
+                  int c, void* stream);
+/* sums: fp32 [2c+1] accumulated (caller zeroes): {sum g, sum g*xhat, sum dout*min(0,z)} */
+int sisr_bn_bwd_reduce(const sisr_bf16* dout, const sisr_bf16* y, const float* mean, const float* invstd,
+                       const float* scale, const float* shift, int act, float slope,
+                       const float* slope_ptr, float* sums, long long rows, int c, void* stream);
+int sisr_bn_bwd_apply(const sisr_bf16* dout, const sisr_bf16* y, const float* mean, const float* invstd,
+                      const float* scale, const float* shift, int act, float slope,
+                      const float* slope_ptr, const float* sums, float count, sisr_bf16* dy,
+                      long long rows, int c, void* stream);
+/* backward of an activation fused in a conv epilogue, from its OUTPUT (needs slope > 0):
+ * din = dout * f'(out); dslope (nullable, accumulated) += sum dout * min(0, pre) */
+int sisr_act_bwd(const sisr_bf16* dout, const sisr_bf16* out, int act, float slope, const float* slope_ptr,
+                 sisr_bf16* din, float* dslope, long long numel, void* stream);
+
+/* ---- MaxPool2d(2,2) of torchvision vgg19.features ---- */
+int sisr_maxpool2_fwd(const sisr_bf16* x, sisr_bf16* y, int n, int h, int w, int c, void* stream);
+int sisr_maxpool2_bwd(const sisr_bf16* x, const sisr_bf16* dy, sisr_bf16* dx, int n, int h, int w, int c,
+                      void* stream);
+
+/* ---- discriminator head: model_discriminator.py:47-53,59-60 ---- */
+int sisr_dhead_forward(const sisr_bf16* x_flat, const float* w0, const float* b0, const float* w2,
+                       const float* b2, float slope, float* h, float* p, int batch, int fc_in, int fc_mid,
+                       void* stream);
+int sisr_dhead_backward(const sisr_bf16* x_flat, const float* w0, const float* w2, const float* h,
+                        const float* p, const float* dp, float slope, float* dh, float* dw0, float* db0,
+                        float* dw2, float* db2, float* dx_flat, int batch, int fc_in, int fc_mid,
+                        int need_wgrad, void* stream);
+
+/* ---- losses: nn.BCELoss (config.py:107; train.py:135,159,177), feature MSE (train.py:183-186) ---- */
+int sisr_bce_fwd(const float* p, int n, float target, float* loss, float* mean_p, void* stream);
+int sisr_bce_bwd(const float* p, int n, float target, const float* gout, float* dp, void* stream);
+/* loss = coef * sum (a-b)^2 ; grads: gb = gout*2*coef*(b-a), ga = -gb (either nullable) */
+int sisr_mse_fwd(const float* a, const float* b, long long n, float coef, float* loss, void* stream);
+int sisr_mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
+                 float* gb, void* stream);
+
+/* ---- optimiser: torch.optim.Adam + LambdaLR (config.py:170-180, 293-294; train.py:75,108,121-122) ---- */
+int sisr_adam_tick(int* step, float lr0, float decay, float b1, float b2, float* hyper, void* stream);
+/* p/g/m/v/numel are HOST arrays of n device pointers / element counts */
+int sisr_adam_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                    const long long* numel, const float* hyper, float b1, float b2, float eps,
+                    float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SISR_B200_H_ */

@@ -91,9 +91,16 @@ __global__ void conv_dgrad_simt_kernel(SimtConv c, const __nv_bfloat16* __restri
 // dw[co,kh,kw,ci] = sum_pixels dy[p,co] * x[p shifted by tap, ci].  One block per (co, tap);
 // threads = groups x channel-chunk, block reduction over the pixel groups.
 constexpr int kWgradThreads = 256;
+__device__ __forceinline__ size_t dy_index(const SimtConv& c, int n, int oh, int ow, int co, int ps_c) {
+  if (ps_c == 0) return (static_cast<size_t>(n * c.OH + oh) * c.OW + ow) * c.Cout + co;
+  const int sub = co / ps_c, ch = co - sub * ps_c;
+  return (static_cast<size_t>(n * 2 * c.OH + 2 * oh + (sub >> 1)) * (2 * c.OW) + 2 * ow + (sub & 1)) *
+             ps_c + ch;
+}
 __global__ void conv_wgrad_simt_kernel(SimtConv c, const __nv_bfloat16* __restrict__ x,
                                        const __nv_bfloat16* __restrict__ dy,
-                                       float* __restrict__ dw, int accumulate) {
+                                       float* __restrict__ dw, float* __restrict__ dbias, int ps_c,
+                                       int accumulate) {
   __shared__ float red[kWgradThreads];
   const int co = blockIdx.x;
   const int tap = blockIdx.y;
@@ -115,7 +122,7 @@ __global__ void conv_wgrad_simt_kernel(SimtConv c, const __nv_bfloat16* __restri
         const int ih = oh * c.stride - c.pad + kh;
         const int iw = ow * c.stride - c.pad + kw;
         if (ih < 0 || ih >= c.H || iw < 0 || iw >= c.W) continue;
-        const float d = __bfloat162float(dy[p * c.Cout + co]);
+        const float d = __bfloat162float(dy[dy_index(c, n, oh, ow, co, ps_c)]);
         const float v =
             __bfloat162float(x[(static_cast<size_t>(n * c.H + ih) * c.W + iw) * c.Cin + ci]);
         acc = fmaf(d, v, acc);
@@ -130,6 +137,22 @@ __global__ void conv_wgrad_simt_kernel(SimtConv c, const __nv_bfloat16* __restri
       *dst = accumulate ? *dst + s : s;
     }
     __syncthreads();
+  }
+  if (dbias && tap == 0) {
+    float acc = 0.f;
+    for (long long p = threadIdx.x; p < npix; p += blockDim.x) {
+      const int ow = static_cast<int>(p % c.OW);
+      const long long t = p / c.OW;
+      acc += __bfloat162float(dy[dy_index(c, static_cast<int>(t / c.OH), static_cast<int>(t % c.OH),
+                                          ow, co, ps_c)]);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int j = 0; j < kWgradThreads; ++j) s += red[j];
+      dbias[co] = accumulate ? dbias[co] + s : s;
+    }
   }
 }
 
@@ -158,9 +181,9 @@ int conv_dgrad_simt(const SimtConv& c, const __nv_bfloat16* dy, const __nv_bfloa
 }
 
 int conv_wgrad_simt(const SimtConv& c, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
-                    int accumulate, cudaStream_t stream) {
+                    float* dbias, int ps_c, int accumulate, cudaStream_t stream) {
   dim3 grid(c.Cout, c.KH * c.KW);
-  conv_wgrad_simt_kernel<<<grid, kWgradThreads, 0, stream>>>(c, x, dy, dw, accumulate);
+  conv_wgrad_simt_kernel<<<grid, kWgradThreads, 0, stream>>>(c, x, dy, dw, dbias, ps_c, accumulate);
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
 

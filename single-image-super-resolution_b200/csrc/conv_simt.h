@@ -19,8 +19,9 @@ int conv_fprop_simt(const SimtConv& c, const __nv_bfloat16* x, const __nv_bfloat
                     __nv_bfloat16* y_bf16, float* y_nchw_f32, cudaStream_t stream);
 int conv_dgrad_simt(const SimtConv& c, const __nv_bfloat16* dy, const __nv_bfloat16* w,
                     __nv_bfloat16* dx, cudaStream_t stream);
-// dw is fp32 [Cout, KH, KW, Cin]
+// dw is fp32 [Cout, KH, KW, Cin]; dbias fp32 [Cout] or null.  ps_c > 0: dy is stored
+// pixel-shuffled as [N, 2*OH, 2*OW, ps_c] and GEMM column co = (i*2+j)*ps_c + c.
 int conv_wgrad_simt(const SimtConv& c, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw,
-                    int accumulate, cudaStream_t stream);
+                    float* dbias, int ps_c, int accumulate, cudaStream_t stream);
 
 }  // namespace sisr

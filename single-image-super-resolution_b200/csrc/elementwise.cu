@@ -1,0 +1,603 @@
+// HBM/L2-bound kernels of the SRGAN step on NHWC bf16 activations:
+// layout conversion at the module boundary, BatchNorm statistics / apply / backward fused with
+// PReLU / LeakyReLU / residual add, activation backward for epilogue-fused activations,
+// 2x2 max-pool, feature-MSE and BCE losses.  16-byte vector accesses, fp32 arithmetic.
+#include "elementwise.h"
+
+#include <stdio.h>
+
+#include "ptx.cuh"
+
+namespace sisr {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Vec8 {
+  float v[8];
+};
+__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  Vec8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
+  uint4 u;
+  u.x = pack_bf16x2(r.v[0], r.v[1]);
+  u.y = pack_bf16x2(r.v[2], r.v[3]);
+  u.z = pack_bf16x2(r.v[4], r.v[5]);
+  u.w = pack_bf16x2(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+  return (act == ACT_NONE || z > 0.f) ? z : z * slope;
+}
+__device__ __forceinline__ float act_grad(float z, int act, float slope) {
+  return (act == ACT_NONE || z > 0.f) ? 1.f : slope;
+}
+__device__ __forceinline__ float resolve_slope(int act, float slope, const float* slope_ptr) {
+  if (act == ACT_PRELU) return *slope_ptr;
+  if (act == ACT_RELU) return 0.f;
+  return slope;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+inline int grid_for(long long work, int threads, int cap = 148 * 16) {
+  long long b = (work + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------ layout conversion
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                             int N, int C, int H, int W) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long p = i / C;
+    const int w = static_cast<int>(p % W);
+    p /= W;
+    const int h = static_cast<int>(p % H);
+    const int n = static_cast<int>(p / H);
+    y[i] = __float2bfloat16_rn(x[((static_cast<long long>(n) * C + c) * H + h) * W + w]);
+  }
+}
+// tiled transpose per image: [HW, C] bf16 -> [C, HW] f32 (and back)
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+                                             int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const __nv_bfloat16* xn = x + static_cast<size_t>(n) * HW * C;
+  float* yn = y + static_cast<size_t>(n) * HW * C;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < HW && c < C) tile[r][threadIdx.x] = __bfloat162float(xn[static_cast<size_t>(p) * C + c]);
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (p < HW && c < C) yn[static_cast<size_t>(c) * HW + p] = tile[threadIdx.x][r];
+  }
+}
+__global__ void nchw_f32_to_nhwc_bf16_tiled_kernel(const float* __restrict__ x,
+                                                   __nv_bfloat16* __restrict__ y, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xn = x + static_cast<size_t>(n) * HW * C;
+  __nv_bfloat16* yn = y + static_cast<size_t>(n) * HW * C;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (p < HW && c < C) tile[r][threadIdx.x] = xn[static_cast<size_t>(c) * HW + p];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < HW && c < C) yn[static_cast<size_t>(p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+  }
+}
+// [HW, C] bf16 <-> [C, HW] bf16 (discriminator flatten order)
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                      int R, int Cc) {
+  // x: [n][R][Cc] -> y: [n][Cc][R]
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const __nv_bfloat16* xn = x + static_cast<size_t>(n) * R * Cc;
+  __nv_bfloat16* yn = y + static_cast<size_t>(n) * R * Cc;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = xn[static_cast<size_t>(r) * Cc + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) yn[static_cast<size_t>(c) * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+// dpre[n,h,w,c] (bf16) = dout[n,c,h,w] * (1 - y[n,c,h,w]^2)
+__global__ void tanh_bwd_nchw_to_nhwc_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                             __nv_bfloat16* __restrict__ dpre, int N, int C, int H,
+                                             int W) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long p = i / C;
+    const int w = static_cast<int>(p % W);
+    p /= W;
+    const int h = static_cast<int>(p % H);
+    const int n = static_cast<int>(p / H);
+    const long long j = ((static_cast<long long>(n) * C + c) * H + h) * W + w;
+    const float yv = y[j];
+    dpre[i] = __float2bfloat16_rn(dout[j] * (1.f - yv * yv));
+  }
+}
+
+// ------------------------------------------------------------------ per-channel reductions
+// stats[0..C) += sum_rows y, stats[C..2C) += sum_rows y^2  (y: [M, C] bf16, C % 8 == 0, C <= 2048)
+__global__ void col_stats_kernel(const __nv_bfloat16* __restrict__ y, long long M, int C,
+                                 float* __restrict__ stats, int with_sq) {
+  extern __shared__ float s_acc[];  // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int tpr = C / 8;
+  const int rpb = blockDim.x / tpr;
+  const int r = threadIdx.x / tpr, cv = threadIdx.x % tpr;
+  float s1[8] = {0}, s2[8] = {0};
+  if (r < rpb) {
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < M;
+         row += static_cast<long long>(gridDim.x) * rpb) {
+      const Vec8 v = load8(y + row * C + cv * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += v.v[j];
+        s2[j] += v.v[j] * v.v[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_acc[cv * 8 + j], s1[j]);
+      if (with_sq) atomicAdd(&s_acc[C + cv * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (with_sq ? 2 * C : C); i += blockDim.x) atomicAdd(&stats[i], s_acc[i]);
+}
+
+// ------------------------------------------------------------------ BatchNorm finalize
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches, float momentum, float eps,
+                                   int training, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    mean = stats[c] / count;
+    var = fmaxf(stats[C + c] / count - mean * mean, 0.f);
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+}
+
+// ------------------------------------------------------------------ BatchNorm apply (+act, +residual)
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, int act, float slope,
+                                const float* __restrict__ slope_ptr,
+                                const __nv_bfloat16* __restrict__ residual,
+                                __nv_bfloat16* __restrict__ out, long long nvec, int C) {
+  const float sl = resolve_slope(act, slope, slope_ptr);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>((i * 8) % C);
+    Vec8 v = load8(y + i * 8);
+    const float4 sc0 = *reinterpret_cast<const float4*>(scale + c0);
+    const float4 sc1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 sh0 = *reinterpret_cast<const float4*>(shift + c0);
+    const float4 sh1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = act_fwd(fmaf(v.v[j], sc[j], sh[j]), act, sl);
+    if (residual) {
+      const Vec8 r = load8(residual + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] += r.v[j];
+    }
+    store8(out + i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm backward
+// sums[0..C) += sum g, sums[C..2C) += sum g*xhat, sums[2C] += sum dout*min(0,z)   (g = dout*act'(z))
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout,
+                                     const __nv_bfloat16* __restrict__ y,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     int act, float slope, const float* __restrict__ slope_ptr,
+                                     float* __restrict__ sums, long long M, int C) {
+  extern __shared__ float s_acc[];  // [2*C + 1]
+  for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const float sl = resolve_slope(act, slope, slope_ptr);
+  const int tpr = C / 8;
+  const int rpb = blockDim.x / tpr;
+  const int r = threadIdx.x / tpr, cv = threadIdx.x % tpr;
+  float s1[8] = {0}, s2[8] = {0}, sa = 0.f;
+  if (r < rpb) {
+    float mu[8], is[8], sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mean[cv * 8 + j];
+      is[j] = invstd[cv * 8 + j];
+      sc[j] = scale[cv * 8 + j];
+      sh[j] = shift[cv * 8 + j];
+    }
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < M;
+         row += static_cast<long long>(gridDim.x) * rpb) {
+      const Vec8 d = load8(dout + row * C + cv * 8);
+      const Vec8 v = load8(y + row * C + cv * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(v.v[j], sc[j], sh[j]);
+        const float g = d.v[j] * act_grad(z, act, sl);
+        s1[j] += g;
+        s2[j] += g * (v.v[j] - mu[j]) * is[j];
+        if (act == ACT_PRELU) sa += d.v[j] * fminf(z, 0.f);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_acc[cv * 8 + j], s1[j]);
+      atomicAdd(&s_acc[C + cv * 8 + j], s2[j]);
+    }
+  }
+  if (act == ACT_PRELU) {
+    sa = warp_sum(sa);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[2 * C], sa);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C + (act == ACT_PRELU ? 1 : 0); i += blockDim.x)
+    atomicAdd(&sums[i], s_acc[i]);
+}
+
+// dy = gamma*invstd * (g - sum_g/count - xhat * sum_gx/count)
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout,
+                                    const __nv_bfloat16* __restrict__ y,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    int act, float slope, const float* __restrict__ slope_ptr,
+                                    const float* __restrict__ sums, float inv_count,
+                                    __nv_bfloat16* __restrict__ dy, long long nvec, int C) {
+  const float sl = resolve_slope(act, slope, slope_ptr);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>((i * 8) % C);
+    const Vec8 d = load8(dout + i * 8);
+    const Vec8 v = load8(y + i * 8);
+    Vec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float sc = scale[c];
+      const float z = fmaf(v.v[j], sc, shift[c]);
+      const float g = d.v[j] * act_grad(z, act, sl);
+      const float xh = (v.v[j] - mean[c]) * invstd[c];
+      o.v[j] = sc * (g - sums[c] * inv_count - xh * sums[C + c] * inv_count);
+    }
+    store8(dy + i * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------ activation backward (from output)
+// din = dout * (out > 0 ? 1 : slope); dslope += sum_{out<0} dout*out/slope   (requires slope > 0)
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                               const __nv_bfloat16* __restrict__ out, int act, float slope,
+                               const float* __restrict__ slope_ptr, __nv_bfloat16* __restrict__ din,
+                               float* __restrict__ dslope, long long nvec) {
+  const float sl = resolve_slope(act, slope, slope_ptr);
+  const float inv_sl = sl != 0.f ? 1.f / sl : 0.f;
+  float sa = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const Vec8 d = load8(dout + i * 8);
+    const Vec8 o = load8(out + i * 8);
+    Vec8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool pos = o.v[j] > 0.f;
+      r.v[j] = pos ? d.v[j] : d.v[j] * sl;
+      if (!pos) sa += d.v[j] * o.v[j] * inv_sl;
+    }
+    store8(din + i * 8, r);
+  }
+  if (dslope) {
+    __shared__ float s_part[kThreads / 32];
+    sa = warp_sum(sa);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sa;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < kThreads / 32 ? s_part[threadIdx.x] : 0.f;
+      t = warp_sum(t);
+      if (threadIdx.x == 0) atomicAdd(dslope, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 2x2 max-pool
+__global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                    int N, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, cv = C / 8;
+  const long long total = static_cast<long long>(N) * OH * OW * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    long long p = i / cv;
+    const int ow = static_cast<int>(p % OW);
+    p /= OW;
+    const int oh = static_cast<int>(p % OH);
+    const int n = static_cast<int>(p / OH);
+    const __nv_bfloat16* b = x + ((static_cast<size_t>(n) * H + oh * 2) * W + ow * 2) * C + c * 8;
+    const Vec8 a0 = load8(b), a1 = load8(b + C), a2 = load8(b + static_cast<size_t>(W) * C),
+               a3 = load8(b + static_cast<size_t>(W) * C + C);
+    Vec8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = fmaxf(fmaxf(a0.v[j], a1.v[j]), fmaxf(a2.v[j], a3.v[j]));
+    store8(y + i * 8, r);
+  }
+}
+// gradient goes to the first maximum in scan order (torch semantics); dx fully written for even H, W
+__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                    const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                    int N, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, cv = C / 8;
+  const long long total = static_cast<long long>(N) * OH * OW * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    long long p = i / cv;
+    const int ow = static_cast<int>(p % OW);
+    p /= OW;
+    const int oh = static_cast<int>(p % OH);
+    const int n = static_cast<int>(p / OH);
+    const size_t base = ((static_cast<size_t>(n) * H + oh * 2) * W + ow * 2) * C + c * 8;
+    const size_t offs[4] = {0, static_cast<size_t>(C), static_cast<size_t>(W) * C,
+                            static_cast<size_t>(W) * C + C};
+    Vec8 a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = load8(x + base + offs[k]);
+    const Vec8 g = load8(dy + i * 8);
+    Vec8 o[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float m = a[0].v[j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (a[k].v[j] > m) {
+          m = a[k].v[j];
+          best = k;
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k].v[j] = (k == best) ? g.v[j] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) store8(dx + base + offs[k], o[k]);
+  }
+}
+
+// ------------------------------------------------------------------ losses
+// loss += weight/n * sum (a-b)^2 ;  (fp32 inputs)
+__global__ void mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                               float coef, float* __restrict__ loss) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = a[i] - b[i];
+    s += d * d;
+  }
+  __shared__ float s_part[kThreads / 32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < kThreads / 32 ? s_part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(loss, t * coef);
+  }
+}
+// grad_b = gout * 2*coef * (b - a),  grad_a = -grad_b
+__global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                               float coef, const float* __restrict__ gout, float* __restrict__ ga,
+                               float* __restrict__ gb) {
+  const float k = 2.f * coef * (*gout);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = (b[i] - a[i]) * k;
+    if (gb) gb[i] = d;
+    if (ga) ga[i] = -d;
+  }
+}
+// BCELoss(mean) against a constant target with torch's clamping; dp = gout * (p-t)/max(p(1-p),1e-12)/n
+__global__ void bce_kernel(const float* __restrict__ p, int n, float target, float* __restrict__ loss,
+                           float* __restrict__ mean_p) {
+  float s = 0.f, sp = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float q = p[i];
+    s -= target * fmaxf(logf(q), -100.f) + (1.f - target) * fmaxf(logf(1.f - q), -100.f);
+    sp += q;
+  }
+  __shared__ float s_part[2][kThreads / 32];
+  s = warp_sum(s);
+  sp = warp_sum(sp);
+  if ((threadIdx.x & 31) == 0) {
+    s_part[0][threadIdx.x >> 5] = s;
+    s_part[1][threadIdx.x >> 5] = sp;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f, tp = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) {
+      t += s_part[0][i];
+      tp += s_part[1][i];
+    }
+    *loss = t / n;
+    if (mean_p) *mean_p = tp / n;
+  }
+}
+__global__ void bce_bwd_kernel(const float* __restrict__ p, int n, float target,
+                               const float* __restrict__ gout, float* __restrict__ dp) {
+  const float g = *gout / n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float q = p[i];
+    dp[i] = g * (q - target) / fmaxf(q * (1.f - q), 1e-12f);
+  }
+}
+
+int check() { return cudaGetLastError() == cudaSuccess ? 0 : 4; }
+
+}  // namespace
+
+int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int N, int C, int H, int W,
+                          cudaStream_t s) {
+  if (C < 32) {
+    const long long total = static_cast<long long>(N) * C * H * W;
+    nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(x, y, N, C, H, W);
+  } else {
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    nchw_f32_to_nhwc_bf16_tiled_kernel<<<grid, block, 0, s>>>(x, y, C, H * W);
+  }
+  return check();
+}
+int nhwc_bf16_to_nchw_f32(const __nv_bfloat16* x, float* y, int N, int C, int H, int W,
+                          cudaStream_t s) {
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, s>>>(x, y, C, H * W);
+  return check();
+}
+int tanh_bwd_nchw_to_nhwc(const float* dout, const float* y, __nv_bfloat16* dpre, int N, int C, int H,
+                          int W, cudaStream_t s) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  tanh_bwd_nchw_to_nhwc_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(dout, y, dpre, N, C, H, W);
+  return check();
+}
+int transpose_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, int batch, int R, int Cc,
+                   cudaStream_t s) {
+  dim3 grid((R + 31) / 32, (Cc + 31) / 32, batch), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, s>>>(x, y, R, Cc);
+  return check();
+}
+int col_stats(const __nv_bfloat16* y, long long M, int C, float* stats, int with_sq, cudaStream_t s) {
+  if (C % 8 || C / 8 > kThreads) return 1;
+  const int rpb = kThreads / (C / 8);
+  col_stats_kernel<<<grid_for(M, rpb, 148 * 4), kThreads, 2 * C * sizeof(float), s>>>(y, M, C, stats,
+                                                                                    with_sq);
+  return check();
+}
+int bn_finalize(const float* stats, float count, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, long long* num_batches, float momentum,
+                float eps, int training, float* scale, float* shift, float* mean, float* invstd, int C,
+                cudaStream_t s) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, count, gamma, beta, running_mean,
+                                                     running_var, num_batches, momentum, eps, training,
+                                                     scale, shift, mean, invstd, C);
+  return check();
+}
+int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, int act, float slope,
+             const float* slope_ptr, const __nv_bfloat16* residual, __nv_bfloat16* out, long long M,
+             int C, cudaStream_t s) {
+  if (C % 8) return 1;
+  const long long nvec = M * C / 8;
+  bn_apply_kernel<<<grid_for(nvec, kThreads), kThreads, 0, s>>>(y, scale, shift, act, slope, slope_ptr,
+                                                                residual, out, nvec, C);
+  return check();
+}
+int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float* mean,
+                  const float* invstd, const float* scale, const float* shift, int act, float slope,
+                  const float* slope_ptr, float* sums, long long M, int C, cudaStream_t s) {
+  if (C % 8 || C / 8 > kThreads) return 1;
+  const int rpb = kThreads / (C / 8);
+  bn_bwd_reduce_kernel<<<grid_for(M, rpb, 148 * 4), kThreads, (2 * C + 1) * sizeof(float), s>>>(
+      dout, y, mean, invstd, scale, shift, act, slope, slope_ptr, sums, M, C);
+  return check();
+}
+int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float* mean,
+                 const float* invstd, const float* scale, const float* shift, int act, float slope,
+                 const float* slope_ptr, const float* sums, float count, __nv_bfloat16* dy,
+                 long long M, int C, cudaStream_t s) {
+  if (C % 8) return 1;
+  const long long nvec = M * C / 8;
+  bn_bwd_apply_kernel<<<grid_for(nvec, kThreads), kThreads, 0, s>>>(
+      dout, y, mean, invstd, scale, shift, act, slope, slope_ptr, sums, 1.f / count, dy, nvec, C);
+  return check();
+}
+int act_bwd(const __nv_bfloat16* dout, const __nv_bfloat16* out, int act, float slope,
+            const float* slope_ptr, __nv_bfloat16* din, float* dslope, long long n, cudaStream_t s) {
+  if (n % 8) return 1;
+  act_bwd_kernel<<<grid_for(n / 8, kThreads, 148 * 8), kThreads, 0, s>>>(dout, out, act, slope,
+                                                                         slope_ptr, din, dslope, n / 8);
+  return check();
+}
+int maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int N, int H, int W, int C,
+                 cudaStream_t s) {
+  if (C % 8 || H % 2 || W % 2) return 1;
+  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_fwd_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(x, y, N, H, W, C);
+  return check();
+}
+int maxpool2_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16* dx, int N, int H,
+                 int W, int C, cudaStream_t s) {
+  if (C % 8 || H % 2 || W % 2) return 1;
+  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_bwd_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(x, dy, dx, N, H, W, C);
+  return check();
+}
+int mse_fwd(const float* a, const float* b, long long n, float coef, float* loss, cudaStream_t s) {
+  cudaMemsetAsync(loss, 0, sizeof(float), s);
+  mse_fwd_kernel<<<grid_for(n, kThreads, 148 * 4), kThreads, 0, s>>>(a, b, n, coef, loss);
+  return check();
+}
+int mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
+            float* gb, cudaStream_t s) {
+  mse_bwd_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(a, b, n, coef, gout, ga, gb);
+  return check();
+}
+int bce_fwd(const float* p, int n, float target, float* loss, float* mean_p, cudaStream_t s) {
+  bce_kernel<<<1, kThreads, 0, s>>>(p, n, target, loss, mean_p);
+  return check();
+}
+int bce_bwd(const float* p, int n, float target, const float* gout, float* dp, cudaStream_t s) {
+  bce_bwd_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(p, n, target, gout, dp);
+  return check();
+}
+
+}  // namespace sisr

@@ -6,7 +6,7 @@
 
 namespace sisr {
 
-constexpr int kMaxTaps = 9;
+constexpr int kMaxTaps = 36;  // 9 filter taps x 4 PixelShuffle sub-pixels (dgrad through the shuffle)
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_PRELU = 3, ACT_TANH = 4 };
 

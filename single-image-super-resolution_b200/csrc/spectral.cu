@@ -1,0 +1,196 @@
+// Spectral-norm power iteration (legacy torch.nn.utils.spectral_norm semantics), weight
+// preparation (1/sigma scaling, [Cout,Cin,kh,kw] fp32 -> [Cout',kh,kw,Cin] bf16 for fprop and
+// [Cin,kh,kw,Cout'] bf16 for dgrad, optional PixelShuffle row permutation) and the mapping of the
+// weight gradient back to the fp32 master layout including the gradient through sigma.
+#include "spectral.h"
+
+#include <stdio.h>
+
+namespace sisr {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += scratch[i];
+  return t;
+}
+
+// t[k] += sum_{co in chunk} W[co,k] * u[co]
+__global__ void sn_wtu_kernel(const float* __restrict__ w, const float* __restrict__ u,
+                              float* __restrict__ t, int Cout, int K, int co_chunk) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int c0 = blockIdx.y * co_chunk;
+  const int c1 = min(Cout, c0 + co_chunk);
+  float acc = 0.f;
+  for (int co = c0; co < c1; ++co) acc = fmaf(w[static_cast<size_t>(co) * K + k], u[co], acc);
+  atomicAdd(&t[k], acc);
+}
+// s[co] = sum_k W[co,k] * t[k]
+__global__ void sn_wv_kernel(const float* __restrict__ w, const float* __restrict__ t,
+                             float* __restrict__ s, int K) {
+  __shared__ float scratch[32];
+  const int co = blockIdx.x;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    acc = fmaf(w[static_cast<size_t>(co) * K + k], t[k], acc);
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) s[co] = acc;
+}
+// training: v = t/|t|, s = s_raw/|t|, u = s/|s|, sigma = u.s ; eval: sigma = u . s_raw (t was v)
+__global__ void sn_finish_kernel(const float* __restrict__ t, const float* __restrict__ s_raw,
+                                 float* __restrict__ u, float* __restrict__ v,
+                                 float* __restrict__ sigma, int Cout, int K, int training, float eps) {
+  __shared__ float scratch[32];
+  if (training) {
+    float a = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) a += t[k] * t[k];
+    const float nt = fmaxf(sqrtf(block_sum(a, scratch)), eps);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) v[k] = t[k] / nt;
+    float b = 0.f;
+    for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+      const float sv = s_raw[c] / nt;
+      b += sv * sv;
+    }
+    const float ss = block_sum(b, scratch);
+    const float ns = fmaxf(sqrtf(ss), eps);
+    for (int c = threadIdx.x; c < Cout; c += blockDim.x) u[c] = (s_raw[c] / nt) / ns;
+    if (threadIdx.x == 0) *sigma = ss / ns;
+  } else {
+    float b = 0.f;
+    for (int c = threadIdx.x; c < Cout; c += blockDim.x) b += u[c] * s_raw[c];
+    b = block_sum(b, scratch);
+    if (threadIdx.x == 0) *sigma = b;
+  }
+}
+
+__device__ __forceinline__ int unpermute_row(int cop, int Cout, int ps_r) {
+  if (ps_r <= 1) return cop;
+  const int r2 = ps_r * ps_r;
+  const int cps = Cout / r2;
+  const int sub = cop / cps, c = cop % cps;
+  return c * r2 + sub;  // PixelShuffle: co = c*r^2 + i*r + j, sub = i*r + j
+}
+
+__global__ void weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ sigma,
+                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ wf,
+                                   __nv_bfloat16* __restrict__ wd, float* __restrict__ bias_perm,
+                                   int Cout, int Cin, int KH, int KW, int ps_r) {
+  const float inv = sigma ? 1.f / *sigma : 1.f;
+  const int taps = KH * KW;
+  const long long total = static_cast<long long>(Cout) * taps * Cin;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const int tap = static_cast<int>((i / Cin) % taps);
+    const int cop = static_cast<int>(i / (static_cast<long long>(Cin) * taps));
+    const int co = unpermute_row(cop, Cout, ps_r);
+    const float val = w[(static_cast<size_t>(co) * Cin + ci) * taps + tap] * inv;
+    const __nv_bfloat16 h = __float2bfloat16_rn(val);
+    wf[i] = h;
+    if (wd) wd[(static_cast<size_t>(ci) * taps + tap) * Cout + cop] = h;
+    if (bias_perm && tap == 0 && ci == 0) bias_perm[cop] = bias[co];
+  }
+}
+
+// dot += sum G .* W_orig   (G given in prepared layout)
+__global__ void wgrad_dot_kernel(const float* __restrict__ gp, const float* __restrict__ w,
+                                 float* __restrict__ dot, int Cout, int Cin, int taps, int ps_r) {
+  __shared__ float scratch[32];
+  const long long total = static_cast<long long>(Cout) * taps * Cin;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const int tap = static_cast<int>((i / Cin) % taps);
+    const int cop = static_cast<int>(i / (static_cast<long long>(Cin) * taps));
+    const int co = unpermute_row(cop, Cout, ps_r);
+    acc = fmaf(gp[i], w[(static_cast<size_t>(co) * Cin + ci) * taps + tap], acc);
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) atomicAdd(dot, acc);
+}
+// dW_orig[co,ci,tap] (+)= G/sigma - dot/sigma^2 * u[co]*v[ci*taps+tap]      (sigma == null: dW = G)
+__global__ void wgrad_finish_kernel(const float* __restrict__ gp, const float* __restrict__ u,
+                                    const float* __restrict__ v, const float* __restrict__ sigma,
+                                    const float* __restrict__ dot, float* __restrict__ dw,
+                                    const float* __restrict__ dbias_perm, float* __restrict__ dbias,
+                                    int Cout, int Cin, int taps, int ps_r, int accumulate) {
+  const float inv = sigma ? 1.f / *sigma : 1.f;
+  const float coef = sigma ? (*dot) * inv * inv : 0.f;
+  const long long total = static_cast<long long>(Cout) * taps * Cin;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const int tap = static_cast<int>((i / Cin) % taps);
+    const int cop = static_cast<int>(i / (static_cast<long long>(Cin) * taps));
+    const int co = unpermute_row(cop, Cout, ps_r);
+    float g = gp[i] * inv;
+    if (sigma) g -= coef * u[co] * v[ci * taps + tap];
+    const size_t o = (static_cast<size_t>(co) * Cin + ci) * taps + tap;
+    dw[o] = accumulate ? dw[o] + g : g;
+    if (dbias && tap == 0 && ci == 0) dbias[co] = accumulate ? dbias[co] + dbias_perm[cop] : dbias_perm[cop];
+  }
+}
+
+inline int grid_for(long long work) {
+  long long b = (work + kThreads - 1) / kThreads;
+  if (b > 148 * 8) b = 148 * 8;
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+int check() { return cudaGetLastError() == cudaSuccess ? 0 : 4; }
+
+}  // namespace
+
+size_t sn_workspace_floats(int Cout, int K) { return static_cast<size_t>(K) + Cout + 4; }
+
+int sn_power_iteration(const float* w, float* u, float* v, float* sigma, int Cout, int K,
+                       int training, float eps, float* ws, cudaStream_t s) {
+  float* t = ws;
+  float* s_raw = ws + K;
+  if (training) {
+    cudaMemsetAsync(t, 0, sizeof(float) * K, s);
+    const int co_chunk = 64;
+    dim3 grid((K + kThreads - 1) / kThreads, (Cout + co_chunk - 1) / co_chunk);
+    sn_wtu_kernel<<<grid, kThreads, 0, s>>>(w, u, t, Cout, K, co_chunk);
+    sn_wv_kernel<<<Cout, kThreads, 0, s>>>(w, t, s_raw, K);
+  } else {
+    sn_wv_kernel<<<Cout, kThreads, 0, s>>>(w, v, s_raw, K);
+  }
+  sn_finish_kernel<<<1, kThreads, 0, s>>>(t, s_raw, u, v, sigma, Cout, K, training, eps);
+  return check();
+}
+
+int weight_prep(const float* w, const float* sigma, const float* bias, __nv_bfloat16* wf,
+                __nv_bfloat16* wd, float* bias_perm, int Cout, int Cin, int KH, int KW, int ps_r,
+                cudaStream_t s) {
+  if (ps_r > 1 && Cout % (ps_r * ps_r)) return 1;
+  const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+  weight_prep_kernel<<<grid_for(total), kThreads, 0, s>>>(w, sigma, bias, wf, wd, bias_perm, Cout, Cin,
+                                                          KH, KW, ps_r);
+  return check();
+}
+
+int weight_grad_finish(const float* gp, const float* w, const float* u, const float* v,
+                       const float* sigma, float* dw, const float* dbias_perm, float* dbias, int Cout,
+                       int Cin, int KH, int KW, int ps_r, int accumulate, float* ws, cudaStream_t s) {
+  const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+  float* dot = ws;
+  if (sigma) {
+    cudaMemsetAsync(dot, 0, sizeof(float), s);
+    wgrad_dot_kernel<<<grid_for(total), kThreads, 0, s>>>(gp, w, dot, Cout, Cin, KH * KW, ps_r);
+  }
+  wgrad_finish_kernel<<<grid_for(total), kThreads, 0, s>>>(gp, u, v, sigma, dot, dw, dbias_perm, dbias,
+                                                           Cout, Cin, KH * KW, ps_r, accumulate);
+  return check();
+}
+
+}  // namespace sisr

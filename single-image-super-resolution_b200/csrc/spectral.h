@@ -1,0 +1,24 @@
+// Internal C++ interface: spectral norm + weight layout preparation (see spectral.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace sisr {
+
+size_t sn_workspace_floats(int Cout, int K);
+// w: [Cout, K] fp32 (K = Cin*kh*kw, native flatten order).  training: one power iteration,
+// u/v updated in place, sigma written.  eval: sigma = u^T W v with the stored vectors.
+int sn_power_iteration(const float* w, float* u, float* v, float* sigma, int Cout, int K,
+                       int training, float eps, float* ws, cudaStream_t s);
+// sigma / bias / wd / bias_perm may be null.  ps_r > 1 permutes rows so that GEMM column
+// (i*r + j)*C/r^2 + c holds PixelShuffle output channel c at sub-pixel (i, j).
+int weight_prep(const float* w, const float* sigma, const float* bias, __nv_bfloat16* wf,
+                __nv_bfloat16* wd, float* bias_perm, int Cout, int Cin, int KH, int KW, int ps_r,
+                cudaStream_t s);
+// gp: gradient w.r.t. the prepared weight, fp32 [Cout', kh, kw, Cin]; dw: [Cout, Cin, kh, kw].
+int weight_grad_finish(const float* gp, const float* w, const float* u, const float* v,
+                       const float* sigma, float* dw, const float* dbias_perm, float* dbias, int Cout,
+                       int Cin, int KH, int KW, int ps_r, int accumulate, float* ws, cudaStream_t s);
+
+}  // namespace sisr

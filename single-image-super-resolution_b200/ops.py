@@ -1,0 +1,432 @@
+"""Autograd operators of the SRGAN step, each a thin wrapper that launches the CUDA kernels of
+``libsisr_b200.so`` through the C ABI on the current stream.
+
+Activations between operators are NHWC bf16 tensors; parameters, statistics and gradients of
+parameters are fp32.  PyTorch supplies device memory, streams and the autograd tape only.
+"""
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, call, query
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_PRELU, ACT_TANH = 0, 1, 2, 3, 4
+LEAKY_SLOPE = 0.01   # nn.LeakyReLU() default used by the reference discriminator
+SN_EPS = 1e-12
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+_skip_param_grads = False
+
+
+@contextlib.contextmanager
+def no_param_grads():
+    """Inside this context the operators do not compute parameter gradients (only data
+    gradients).  Used for the discriminator pass of the generator update: the reference computes a
+    D weight gradient there that ``net_d.zero_grad()`` discards before any use (train.py:58,107)."""
+    global _skip_param_grads
+    prev, _skip_param_grads = _skip_param_grads, True
+    try:
+        yield
+    finally:
+        _skip_param_grads = prev
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.SisrError(f"{what}: tensor is on {t.device}; the sisr_b200 operators run only on "
+                             "CUDA (sm_100a) - there is no CPU path")
+
+
+_dist_group = None
+
+
+def set_sync_group(group):
+    """Process group used for SyncBN statistic reductions (None = single process)."""
+    global _dist_group
+    _dist_group = group
+
+
+def _world():
+    import torch.distributed as dist
+    if _dist_group is None or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(_dist_group)
+
+
+def _all_reduce(t):
+    import torch.distributed as dist
+    dist.all_reduce(t, group=_dist_group)
+
+
+# ----------------------------------------------------------------------------- layout
+class ToNHWC(torch.autograd.Function):
+    """NCHW fp32 (module boundary) -> NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x, "ToNHWC")
+        x = x.contiguous().float()
+        n, c, h, w = x.shape
+        y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+        call("sisr_nchw_f32_to_nhwc_bf16", x, y, n, c, h, w, _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = gy.contiguous()
+        n, h, w, c = gy.shape
+        gx = torch.empty((n, c, h, w), dtype=torch.float32, device=gy.device)
+        call("sisr_nhwc_bf16_to_nchw_f32", gy, gx, n, c, h, w, _stream())
+        return gx
+
+
+class ToNCHW(torch.autograd.Function):
+    """NHWC bf16 -> NCHW fp32 (module boundary)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        call("sisr_nhwc_bf16_to_nchw_f32", x, y, n, c, h, w, _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = gy.contiguous().float()
+        n, c, h, w = gy.shape
+        gx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=gy.device)
+        call("sisr_nchw_f32_to_nhwc_bf16", gy, gx, n, c, h, w, _stream())
+        return gx
+
+
+# ----------------------------------------------------------------------------- convolution
+@dataclass(frozen=True)
+class ConvCfg:
+    stride: int = 1
+    pad: int = 1
+    act: int = ACT_NONE
+    leaky_slope: float = LEAKY_SLOPE
+    ps_r: int = 0              # 2: PixelShuffle(2) folded into the store
+    want_stats: bool = False   # BN batch statistics from the conv epilogue
+    training: bool = True      # spectral-norm power iteration on/off
+    out_nchw_f32: bool = False  # edge layer: write fp32 NCHW (+tanh) for the module boundary
+
+
+def _desc(x_shape, cout, k, cfg: ConvCfg) -> ConvDesc:
+    n, h, w, cin = x_shape
+    oh = (h + 2 * cfg.pad - k) // cfg.stride + 1
+    ow = (w + 2 * cfg.pad - k) // cfg.stride + 1
+    return ConvDesc(n, h, w, cin, oh, ow, cout, k, cfg.stride, cfg.pad, cfg.ps_r)
+
+
+class Conv2dFn(torch.autograd.Function):
+    """[spectral norm ->] conv2d + bias [+ PReLU/LeakyReLU/ReLU/Tanh] [+ PixelShuffle(2) store]
+    [+ BN statistics].  ``weight`` is the fp32 master weight ([Cout,Cin,k,k]; ``weight_orig`` when
+    ``u``/``v`` are given).  Returns (y, stats)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, u, v, slope, cfg: ConvCfg, prepared=None):
+        _require_cuda(x, "Conv2dFn")
+        x = x.contiguous()
+        dev = x.device
+        cout, cin, k, _ = weight.shape
+        d = _desc(x.shape, cout, k, cfg)
+        st = _stream()
+        sigma = None
+        if u is not None:
+            sigma = torch.empty(1, dtype=torch.float32, device=dev)
+            ws = torch.empty(query("sisr_sn_workspace_floats", cout, cin * k * k), dtype=torch.float32,
+                             device=dev)
+            call("sisr_sn_power_iteration", weight, u, v, sigma, cout, cin * k * k,
+                 1 if cfg.training else 0, SN_EPS, ws, st)
+        need_dx = x.requires_grad
+        bias_used = bias
+        if prepared is not None:       # frozen weights prepared once by the caller (MaskedVGG)
+            wf, wd = prepared
+        else:
+            wf = torch.empty((cout, k, k, cin), dtype=torch.bfloat16, device=dev)
+            wd = torch.empty((cin, k, k, cout), dtype=torch.bfloat16, device=dev) if need_dx else None
+            if cfg.ps_r == 2:
+                bias_used = torch.empty_like(bias)
+            call("sisr_weight_prep", weight, sigma, bias, wf, wd, bias_used if cfg.ps_r == 2 else None,
+                 cout, cin, k, cfg.ps_r, st)
+        stats = torch.empty(2 * cout, dtype=torch.float32, device=dev) if cfg.want_stats else None
+        if cfg.out_nchw_f32:
+            y = torch.empty((d.n, cout, d.oh, d.ow), dtype=torch.float32, device=dev)
+            call("sisr_conv_fprop", d, x, wf, bias_used, cfg.act, cfg.leaky_slope, slope, None, y, None, st)
+        else:
+            if cfg.ps_r == 2:
+                y = torch.empty((d.n, d.oh * 2, d.ow * 2, cout // 4), dtype=torch.bfloat16, device=dev)
+            else:
+                y = torch.empty((d.n, d.oh, d.ow, cout), dtype=torch.bfloat16, device=dev)
+            call("sisr_conv_fprop", d, x, wf, bias_used, cfg.act, cfg.leaky_slope, slope, y, None, stats, st)
+        ctx.cfg, ctx.d = cfg, d
+        ctx.has_sn = u is not None
+        ctx.has_slope = slope is not None
+        ctx.skip_params = _skip_param_grads
+        saved_u = u.clone() if u is not None else None
+        saved_v = v.clone() if v is not None else None
+        ctx.save_for_backward(x, weight, wf, wd, y if cfg.act != ACT_NONE else None, sigma, saved_u,
+                              saved_v, slope)
+        if stats is not None:
+            ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, gy, _gstats):
+        x, weight, wf, wd, y, sigma, u, v, slope = ctx.saved_tensors
+        cfg, d = ctx.cfg, ctx.d
+        dev = x.device
+        st = _stream()
+        cout, cin, k, _ = weight.shape
+        gy = gy.contiguous()
+        dslope = None
+        if cfg.out_nchw_f32:
+            dpre = torch.empty((d.n, d.oh, d.ow, cout), dtype=torch.bfloat16, device=dev)
+            if cfg.act == ACT_TANH:
+                call("sisr_tanh_bwd_nchw_to_nhwc", gy.float(), y, dpre, d.n, cout, d.oh, d.ow, st)
+            else:
+                call("sisr_nchw_f32_to_nhwc_bf16", gy.float(), dpre, d.n, cout, d.oh, d.ow, st)
+        elif cfg.act != ACT_NONE:
+            dpre = torch.empty_like(gy)
+            want_ds = cfg.act == ACT_PRELU and ctx.needs_input_grad[5] and not ctx.skip_params
+            if want_ds:
+                dslope = torch.zeros(1, dtype=torch.float32, device=dev)
+            call("sisr_act_bwd", gy, y, cfg.act, cfg.leaky_slope, slope, dpre, dslope, gy.numel(), st)
+        else:
+            dpre = gy
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("sisr_conv_dgrad", d, dpre, wf, wd, dx, st)
+        dw = db = None
+        if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not ctx.skip_params:
+            gp = torch.empty((cout, k, k, cin), dtype=torch.float32, device=dev)
+            dbp = torch.empty(cout, dtype=torch.float32, device=dev)
+            nbytes = query("sisr_conv_wgrad_workspace_bytes", d)
+            ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dev)
+            call("sisr_conv_wgrad", d, x, dpre, gp, dbp, ws, st)
+            dw = torch.empty_like(weight)
+            db = torch.empty(cout, dtype=torch.float32, device=dev)
+            ws2 = torch.empty(4, dtype=torch.float32, device=dev)
+            call("sisr_weight_grad_finish", gp, weight, u, v, sigma if ctx.has_sn else None, dw, dbp, db,
+                 cout, cin, k, cfg.ps_r, 0, ws2, st)
+            if not ctx.needs_input_grad[1]:
+                dw = None
+            if not ctx.needs_input_grad[2]:
+                db = None
+        return dx, dw, db, None, None, dslope, None, None
+
+
+# ----------------------------------------------------------------------------- BatchNorm (+act, +residual)
+@dataclass(frozen=True)
+class BnCfg:
+    act: int = ACT_NONE
+    leaky_slope: float = LEAKY_SLOPE
+    training: bool = True
+    momentum: float = BN_MOMENTUM
+    eps: float = BN_EPS
+    sync: bool = True          # reduce statistics over the data-parallel group when one is set
+
+
+class BnActFn(torch.autograd.Function):
+    """out = act(BatchNorm(y)) [+ residual] on NHWC bf16; ``stats`` = per-channel {sum, sum sq} of
+    ``y`` from the producing conv's epilogue (computed here when None)."""
+
+    @staticmethod
+    def forward(ctx, y, stats, gamma, beta, running_mean, running_var, nbt, residual, slope, cfg: BnCfg):
+        y = y.contiguous()
+        dev = y.device
+        c = y.shape[-1]
+        rows = y.numel() // c
+        st = _stream()
+        count = float(rows)
+        if cfg.training:
+            if stats is None:
+                stats = torch.empty(2 * c, dtype=torch.float32, device=dev)
+                call("sisr_bn_stats", y, rows, c, stats, st)
+            world = _world() if cfg.sync else 1
+            if world > 1:
+                stats = stats.clone()
+                _all_reduce(stats)
+                count *= world
+        else:
+            stats = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+        aux = torch.empty((4, c), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
+        call("sisr_bn_finalize", stats, count, gamma, beta, running_mean, running_var, nbt,
+             cfg.momentum, cfg.eps, 1 if cfg.training else 0, aux[0], aux[1], aux[2], aux[3], c, st)
+        out = torch.empty_like(y)
+        if residual is not None:
+            residual = residual.contiguous()
+        call("sisr_bn_apply", y, aux[0], aux[1], cfg.act, cfg.leaky_slope, slope, residual, out, rows, c, st)
+        ctx.cfg, ctx.count = cfg, count
+        ctx.has_residual = residual is not None
+        ctx.skip_params = _skip_param_grads
+        ctx.save_for_backward(y, aux, slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        y, aux, slope = ctx.saved_tensors
+        cfg = ctx.cfg
+        dev = y.device
+        c = y.shape[-1]
+        rows = y.numel() // c
+        st = _stream()
+        gout = gout.contiguous()
+        sums = torch.zeros(2 * c + 1, dtype=torch.float32, device=dev)
+        call("sisr_bn_bwd_reduce", gout, y, aux[2], aux[3], aux[0], aux[1], cfg.act, cfg.leaky_slope,
+             slope, sums, rows, c, st)
+        local = sums
+        if cfg.training:
+            if cfg.sync and _world() > 1:
+                sums = sums.clone()
+                _all_reduce(sums)
+            red = sums
+        else:
+            red = torch.zeros_like(sums)   # eval mode: statistics are constants
+        dy = None
+        if ctx.needs_input_grad[0]:
+            dy = torch.empty_like(y)
+            call("sisr_bn_bwd_apply", gout, y, aux[2], aux[3], aux[0], aux[1], cfg.act, cfg.leaky_slope,
+                 slope, red, ctx.count, dy, rows, c, st)
+        dgamma = dbeta = dslope = None
+        if not ctx.skip_params:
+            if ctx.needs_input_grad[2]:
+                dgamma = local[c:2 * c].clone()
+            if ctx.needs_input_grad[3]:
+                dbeta = local[:c].clone()
+            if slope is not None and ctx.needs_input_grad[8]:
+                dslope = local[2 * c:2 * c + 1].clone()
+        dres = gout if (ctx.has_residual and ctx.needs_input_grad[7]) else None
+        return dy, None, dgamma, dbeta, None, None, None, dres, dslope, None
+
+
+# ----------------------------------------------------------------------------- pooling
+class MaxPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        y = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+        call("sisr_maxpool2_fwd", x, y, n, h, w, c, _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        n, h, w, c = x.shape
+        dx = torch.empty_like(x)
+        call("sisr_maxpool2_bwd", x, gy.contiguous(), dx, n, h, w, c, _stream())
+        return dx
+
+
+# ----------------------------------------------------------------------------- discriminator head
+class DHeadFn(torch.autograd.Function):
+    """flatten (reference (c,h,w) order) -> Linear -> LeakyReLU -> Linear -> Sigmoid; x is NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w2, b2):
+        x = x.contiguous()
+        dev = x.device
+        n, h, w, c = x.shape
+        fc_in, fc_mid = h * w * c, w0.shape[0]
+        st = _stream()
+        xf = torch.empty((n, fc_in), dtype=torch.bfloat16, device=dev)
+        call("sisr_transpose_bf16", x, xf, n, h * w, c, st)
+        hbuf = torch.empty((n, fc_mid), dtype=torch.float32, device=dev)
+        p = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        call("sisr_dhead_forward", xf, w0, b0, w2, b2, LEAKY_SLOPE, hbuf, p, n, fc_in, fc_mid, st)
+        ctx.shape = (n, h, w, c)
+        ctx.skip_params = _skip_param_grads
+        ctx.save_for_backward(xf, w0, w2, hbuf, p)
+        return p
+
+    @staticmethod
+    def backward(ctx, gp):
+        xf, w0, w2, hbuf, p = ctx.saved_tensors
+        n, h, w, c = ctx.shape
+        dev = xf.device
+        fc_in, fc_mid = xf.shape[1], w0.shape[0]
+        st = _stream()
+        need_w = any(ctx.needs_input_grad[1:]) and not ctx.skip_params
+        dh = torch.empty((n, fc_mid), dtype=torch.float32, device=dev)
+        dw0 = torch.empty_like(w0) if need_w else None
+        db0 = torch.empty(fc_mid, dtype=torch.float32, device=dev)
+        dw2 = torch.empty((1, fc_mid), dtype=torch.float32, device=dev)
+        db2 = torch.empty(1, dtype=torch.float32, device=dev)
+        dxf = torch.empty((n, fc_in), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        call("sisr_dhead_backward", xf, w0, w2, hbuf, p, gp.contiguous().float(), LEAKY_SLOPE, dh, dw0,
+             db0, dw2, db2, dxf, n, fc_in, fc_mid, 1 if need_w else 0, st)
+        dx = None
+        if dxf is not None:
+            dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
+            call("sisr_nchw_f32_to_nhwc_bf16", dxf, dx, n, c, h, w, st)
+        if not need_w:
+            return dx, None, None, None, None
+        return dx, dw0, db0, dw2, db2
+
+
+# ----------------------------------------------------------------------------- losses
+class BCEFn(torch.autograd.Function):
+    """nn.BCELoss(reduction='mean') of probabilities ``p`` against a constant target."""
+
+    @staticmethod
+    def forward(ctx, p, target: float):
+        p = p.contiguous().float().view(-1)
+        loss = torch.empty(1, dtype=torch.float32, device=p.device)
+        mean_p = torch.empty(1, dtype=torch.float32, device=p.device)
+        call("sisr_bce_fwd", p, p.numel(), float(target), loss, mean_p, _stream())
+        ctx.target = float(target)
+        ctx.save_for_backward(p)
+        ctx.mark_non_differentiable(mean_p)
+        return loss.view(()), mean_p.view(())
+
+    @staticmethod
+    def backward(ctx, gl, _gm):
+        (p,) = ctx.saved_tensors
+        dp = torch.empty_like(p)
+        call("sisr_bce_bwd", p, p.numel(), ctx.target, gl.contiguous().float().view(1), dp, _stream())
+        return dp, None
+
+
+class MSEFn(torch.autograd.Function):
+    """torch.mean((a - b)**2) on fp32 tensors of equal shape (train.py:186)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous().float(), b.contiguous().float()
+        n = a.numel()
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        call("sisr_mse_fwd", a, b, n, 1.0 / n, loss, _stream())
+        ctx.save_for_backward(a, b)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gl):
+        a, b = ctx.saved_tensors
+        n = a.numel()
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        call("sisr_mse_bwd", a, b, n, 1.0 / n, gl.contiguous().float().view(1), ga, gb, _stream())
+        return ga, gb
+
+
+def bce_loss(p: torch.Tensor, target: float):
+    return BCEFn.apply(p, target)
+
+
+def mse_loss(a: torch.Tensor, b: torch.Tensor):
+    return MSEFn.apply(a, b)

@@ -1,0 +1,143 @@
+"""The SRGAN training step (reference: train.py:33-122, 128-186), same order of operations:
+
+  fake = G(lr)
+  D update : BCE(D(real), 0.9) + sum over [fake.detach(), replayed fakes] of BCE(D(.), 0) -> Adam
+  G update : 5e-2 * BCE(D(fake), 1) + 1.0 * mean((E(real) - E(fake))**2)               -> Adam
+
+Differences that do not change results: no ``.item()`` host syncs inside the step (losses are
+returned as device scalars), the replay list lives on the GPU, and the D weight gradient of the
+G-update pass - which ``net_d.zero_grad()`` discards before any use - is not computed.
+The whole step can be captured into one CUDA graph (``SRGANTrainer.capture``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .optim import Adam
+
+
+@dataclass
+class StepConfig:
+    """Knobs of config.py that shape the step (config.py:38,49-54,136-164,186-188)."""
+    lr: float = 1e-5
+    betas: tuple = (0.9, 0.999)
+    lr_decay_per_step: float = 1.0
+    loss_weight_adv_g: float = 5e-2
+    loss_weight_adv_d: float = 1.0
+    loss_weight_cont: float = 1.0
+    real_label: float = 1.0
+    real_label_reduced: float = 0.9
+    fake_label: float = 0.0
+    dis_list_old_len: int = 1000
+    dis_list_old_freq: int = 1
+    dis_list_old_ratio: float = 0.01
+    use_replay: bool = True
+
+
+class SRGANTrainer:
+    def __init__(self, net_g, net_d, extractor, cfg: Optional[StepConfig] = None, grad_sync=None):
+        self.net_g, self.net_d, self.extractor = net_g, net_d, extractor
+        self.cfg = cfg or StepConfig()
+        c = self.cfg
+        self.opt_g = Adam([p for p in net_g.parameters()], lr=c.lr, betas=c.betas,
+                          decay_per_step=c.lr_decay_per_step)
+        self.opt_d = Adam([p for p in net_d.parameters()], lr=c.lr, betas=c.betas,
+                          decay_per_step=c.lr_decay_per_step)
+        self.dis_list_old: List[torch.Tensor] = []
+        self.iteration = 0
+        self.grad_sync = grad_sync      # parallel.GradSync or None
+        self._graph = None
+        self._static = None
+
+    # -- losses (train.py:128-186) -----------------------------------------------------------
+    def adversarial_loss_d(self, real, curr_fake, old_fakes):
+        c = self.cfg
+        d_real = self.net_d(real).view(-1)
+        err, d_x = ops.bce_loss(d_real, c.real_label_reduced)
+        d_g_z1 = 0
+        for fk in [curr_fake, *old_fakes]:
+            d_fake = self.net_d(fk).view(-1)
+            e, m = ops.bce_loss(d_fake, c.fake_label)
+            err = err + e
+            d_g_z1 = d_g_z1 + m
+        return d_g_z1, d_x, err
+
+    def adversarial_loss_g(self, fake):
+        with ops.no_param_grads():
+            out = self.net_d(fake).view(-1)
+        err, d_g_z2 = ops.bce_loss(out, self.cfg.real_label)
+        return d_g_z2, err
+
+    def content_loss_g(self, real, fake):
+        a = self.extractor(real)
+        b = self.extractor(fake)
+        return ops.mse_loss(a, b)
+
+    # -- one iteration -----------------------------------------------------------------------
+    def step(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=()):
+        """img_hr: (B,3,H,H) fp32 in [-1,1]; img_lr: (B,3,H/s,H/s).  Returns device scalars."""
+        c = self.cfg
+        fake = self.net_g(img_lr)
+
+        self.net_d.zero_grad(set_to_none=True)
+        curr_fake = fake.detach()
+        d_g_z1, d_x, err_d = self.adversarial_loss_d(img_hr, curr_fake, old_fakes)
+        err_d = err_d * c.loss_weight_adv_d
+        err_d.backward()
+        if self.grad_sync is not None:
+            self.grad_sync.sync(self.opt_d)
+        self.opt_d.step()
+
+        self.net_g.zero_grad(set_to_none=True)
+        d_g_z2, err_g_adv = self.adversarial_loss_g(fake)
+        err_g_adv = err_g_adv * c.loss_weight_adv_g
+        err_g_cont = self.content_loss_g(img_hr, fake) * c.loss_weight_cont
+        (err_g_adv + err_g_cont).backward()
+        if self.grad_sync is not None:
+            self.grad_sync.sync(self.opt_g)
+        self.opt_g.step()
+        return {"fake": curr_fake, "err_d": err_d.detach(), "err_g_adv": err_g_adv.detach(),
+                "err_g_cont": err_g_cont.detach(), "d_x": d_x, "d_g_z1": d_g_z1, "d_g_z2": d_g_z2}
+
+    def train_iteration(self, img_hr, img_lr):
+        """step() plus the reference's experience replay bookkeeping (train.py:59-71,144-146)."""
+        import random
+        c = self.cfg
+        old = []
+        if c.use_replay and self.dis_list_old:
+            k = int(len(self.dis_list_old) * c.dis_list_old_ratio)
+            old = [self.dis_list_old[i].float() for i in random.sample(range(len(self.dis_list_old)), k)]
+        out = self.step(img_hr, img_lr, old)
+        if c.use_replay and self.iteration % c.dis_list_old_freq == 0:
+            snap = out["fake"].to(torch.bfloat16)      # replay list kept on the GPU in bf16
+            if len(self.dis_list_old) == c.dis_list_old_len:
+                self.dis_list_old[random.randint(0, c.dis_list_old_len - 1)] = snap
+            else:
+                self.dis_list_old.append(snap)
+        self.iteration += 1
+        return out
+
+    # -- CUDA graph of the whole step ----------------------------------------------------------
+    def capture(self, img_hr: torch.Tensor, img_lr: torch.Tensor, warmup: int = 2):
+        """Capture ``step`` (no replayed fakes) into one CUDA graph with static input buffers."""
+        self._static = (img_hr.clone(), img_lr.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self.step(*self._static)
+        return self._graph_out
+
+    def replay(self, img_hr: torch.Tensor, img_lr: torch.Tensor):
+        self._static[0].copy_(img_hr, non_blocking=True)
+        self._static[1].copy_(img_lr, non_blocking=True)
+        self._graph.replay()
+        return self._graph_out

@@ -1,0 +1,12 @@
+"""Import shim: exposes the hyphenated package directory ``single-image-super-resolution_b200`` as
+the importable package ``sisr_b200`` (``import sisr_b200``)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "single-image-super-resolution_b200")
+_spec = importlib.util.spec_from_file_location(
+    "sisr_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["sisr_b200"] = _mod
+_spec.loader.exec_module(_mod)
