@@ -1,0 +1,317 @@
+"""Benchmark of the SRGAN x4 training step (BASELINE.json metric: HR patches / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+N = 1 workload = BASELINE.json configs[1]: full x4 step (G = GeneratorSuffix(Generator(16 blocks)),
+D at 3x96x96, MaskedVGG54 content loss + adversarial loss), 96x96 HR patches, batch 64 per GPU,
+bf16 storage / fp32 accumulate, synthetic U[-1,1] patches, random-init weights.  N > 1 (launched by
+torchrun, one rank per GPU): same per-GPU batch (weak scaling), NCCL gradient all-reduce + SyncBN.
+
+One JSON line on stdout (rank 0).  ``value`` = patches/s with the batch resident in HBM (whole step
+replayed as one CUDA graph at N = 1); ``e2e`` = the same step fed from pinned HOST buffers with the
+H2D copy of HR+LR and a D2H read of the three losses inside the timed region; ``roofline`` = the
+dominant kernel (tcgen05 implicit-GEMM conv) timed alone with CUDA events against the measured bf16
+peak; ``cpu_baseline`` = the CPU oracle port of the reference step on the box's host cores.
+``--impl reference`` times the reference's own CPU implementation of the step (the oracle port:
+/root/reference does not exist on the GPU box) with all host threads on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PATCH = 42.55e9          # 3 F_G + 8 F_D + 3 F_V at 96x96
+D_FEATS = [64, 64, 128, 128, 256, 256, 512, 512]
+D_STRIDES = [1, 2, 1, 2, 1, 2, 1, 2]
+VGG54 = 0b10000
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "hbm": p["hbm_gbs"], "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6
+                          for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_step_time(batch, steps, warmup, threads):
+    """Seconds per step of the oracle port of train.train_loop's body on the host cores."""
+    import torch
+    from oracle import srgan_oracle as O
+    from oracle import state_factory as S
+    torch.set_num_threads(threads)
+    g = S.generator_state(1, n_blocks=16, n_suffix=1)
+    d = S.discriminator_state(2, (3, 96, 96), D_FEATS, D_STRIDES)
+    v = S.vgg_state(3, VGG54)
+    og = O.AdamState(O.trainable_names(g), 1e-5)
+    od = O.AdamState(O.trainable_names(d), 1e-5)
+    times = []
+    for i in range(warmup + steps):
+        hr = S.synthetic_hr(10 + i, batch, 96)
+        lr = O.lr_from_hr(hr, (24, 24))
+        t0 = time.perf_counter()
+        O.train_step(g, d, v, hr, lr, d_strides=D_STRIDES, vgg_mask=VGG54, opt_g=og, opt_d=od)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 16                                   # bounded sample of the B=64 workload
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    sec = cpu_reference_step_time(batch, steps, warmup, threads)
+    value = batch / sec
+    line = {
+        "impl": "reference", "metric": "SRGAN x4 train-step HR patches/sec", "value": value,
+        "unit": "patches/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SRGAN x4 full training step (G+D+MaskedVGG54), 96x96 HR, CPU fp32, "
+                               f"sample batch {batch} of the batch-64 workload", "spectral_norm": True},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} step(s) of batch {batch} after {warmup} warm-up, oracle port "
+                                   "of train.train_loop body (reference not present on the GPU box)"},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+def build_trainer(dev, batch, world, grad_sync=None):
+    import torch
+    import sisr_b200 as m
+    torch.manual_seed(0)
+    net_g = m.GeneratorSuffix(m.Generator(16, 64, 256, [2], use_sn=True)).to(dev)
+    net_d = m.Discriminator((3, 96, 96), D_FEATS, D_STRIDES).to(dev)
+    ext = m.MaskedVGG(VGG54).to(dev)
+    if world > 1:
+        from sisr_b200 import parallel
+        for net in (net_g, net_d, ext):
+            parallel.broadcast_module(net)
+    tr = m.SRGANTrainer(net_g, net_d, ext, m.StepConfig(lr=1e-5, use_replay=False), grad_sync=grad_sync)
+    if grad_sync is not None:
+        grad_sync.attach(tr.opt_d)
+        grad_sync.attach(tr.opt_g)
+    return tr
+
+
+def time_dominant_kernel(dev, batch, iters=20):
+    """CUDA-event timing of the tcgen05 implicit-GEMM conv on the layer with the largest FLOP share
+    of the step (VGG conv3_x: 256->256 at 24x24), launched alone through the C ABI."""
+    import torch
+    from sisr_b200 import _lib
+    n, h, w, cin, cout = batch, 24, 24, 256, 256
+    x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, 3, 3, cin, device=dev) * 0.02).to(torch.bfloat16)
+    bias = torch.zeros(cout, device=dev)
+    y = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+    d = _lib.ConvDesc(n, h, w, cin, h, w, cout, 3, 1, 1, 0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ms = []
+    for i in range(iters + 3):
+        flush.zero_()                                  # evict L2 (126 MB) between launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("sisr_conv_fprop", d, x, wt, bias, 1, 0.0, None, y, None, None, st)
+        e1.record()
+        e1.synchronize()
+        if i >= 3:
+            ms.append(e0.elapsed_time(e1))
+    flops = 2.0 * n * h * w * cout * 9 * cin
+    avg = sum(ms) / len(ms)
+    return {"kernel": "igemm_tc_kernel<256,4> (conv3x3 256->256 @24x24, batch %d)" % n,
+            "flops": flops, "ms": avg, "tflops": flops / (avg * 1e-3) / 1e12}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sisr_b200 as m  # noqa: F401
+    from sisr_b200 import _lib, parallel
+    from oracle import state_factory as S   # synthetic patch recipe only (host side)
+
+    rank, local, world = parallel.init_distributed()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    batch = args.batch
+    use_graph = (world == 1) and not args.no_graph
+    gs = parallel.GradSync() if world > 1 else None
+    tr = build_trainer(dev, batch, world, gs)
+    hr_host = S.synthetic_hr(1234 + rank, batch, 96).pin_memory()
+    import torch.nn.functional as F
+    lr_host = F.interpolate(hr_host, (24, 24), mode="bicubic", align_corners=True).clamp(-1, 1).pin_memory()
+    hr, lr = hr_host.to(dev), lr_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    calls_before = _lib.LAUNCHES[0] if hasattr(_lib, "LAUNCHES") else 0
+    if use_graph:
+        tr.capture(hr, lr, warmup=2)
+        step = lambda: tr.replay(hr, lr)         # noqa: E731
+    else:
+        step = lambda: tr.step(hr, lr)           # noqa: E731
+    launches_per_step = None
+    if hasattr(_lib, "LAUNCHES"):
+        c0 = _lib.LAUNCHES[0]
+        if use_graph:
+            launches_per_step = (c0 - calls_before) // 3    # 2 warm-up steps + 1 captured step
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: device-resident inputs (inputs > L2? no: 126 MB L2 is flushed by the step
+    # itself: one step touches > 1 GB of activations and weights)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if not use_graph and hasattr(_lib, "LAUNCHES"):
+        c0 = _lib.LAUNCHES[0]
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if not use_graph and hasattr(_lib, "LAUNCHES"):
+        launches_per_step = (_lib.LAUNCHES[0] - c0) // args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    # ---- timed region 2: end to end from pinned host buffers
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    losses = None
+    for _ in range(args.steps):
+        hr.copy_(hr_host, non_blocking=True)
+        lr.copy_(lr_host, non_blocking=True)
+        out = step()
+        losses = torch.stack([out["err_d"].reshape(()), out["err_g_adv"].reshape(()),
+                              out["err_g_cont"].reshape(())]).cpu()      # D2H + sync
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+    peaks = measured_peaks()
+    dom = time_dominant_kernel(dev, batch)
+    total_patches = batch * world * args.steps
+    value = total_patches / (ms * 1e-3)
+    line = {
+        "metric": "SRGAN x4 train-step HR patches/sec", "value": value, "unit": "patches/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "SRGAN x4 full training step (G 16 blocks + suffix, D @3x96x96, "
+                               "MaskedVGG54 content loss + adversarial loss), 96x96 HR patches",
+                   "batch_per_gpu": batch, "global_batch": batch * world, "spectral_norm": True,
+                   "parallelism": f"dp{world}" + (" + SyncBN" if world > 1 else ""),
+                   "cuda_graph": use_graph,
+                   "l2": "one step streams > 1 GB of activations/weights (> 126 MB L2) between reuses"},
+        "step_tflops": FLOP_PER_PATCH * batch / (ms / args.steps * 1e-3) / 1e12,
+        "step_frac_of_sustained_bf16": FLOP_PER_PATCH * batch / (ms / args.steps * 1e-3) / 1e12
+        / peaks["bf16_sustained"],
+        "losses": [float(x) for x in losses],
+        "clocks": clocks,
+        "e2e": {"value": total_patches / (ms_e2e * 1e-3), "unit": "patches/s",
+                "h2d_bytes_per_step": (hr_host.numel() + lr_host.numel()) * 4,
+                "d2h_bytes_per_step": 12},
+        "gpu_launches": (launches_per_step or 0) * args.steps,
+        "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_burst"],
+                     "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["bf16_burst"], "traffic": None,
+                     "kernel": dom["kernel"], "ms_per_launch": dom["ms"], "peak_source": peaks["source"],
+                     "l2_flushed_between_launches": True},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sec = cpu_reference_step_time(8, 1, 1, threads)
+        line["cpu_baseline"] = {"value": 8 / sec, "unit": "patches/s", "cores": threads, "kind": "port",
+                                "sample": "1 step of batch 8 after 1 warm-up step (oracle port of the "
+                                          "reference step, fp32, all host threads)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

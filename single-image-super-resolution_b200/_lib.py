@@ -81,9 +81,16 @@ def _conv(a):
     return a
 
 
+# kernels launched per ABI call (for bench.py's ``gpu_launches`` claim); default 1
+_KERNELS_PER_CALL = {"sisr_sn_power_iteration": 3, "sisr_weight_grad_finish": 2, "sisr_dhead_forward": 2,
+                     "sisr_dhead_backward": 3, "sisr_adam_multi": 2}
+LAUNCHES = [0]
+
+
 def call(name: str, *args):
     """Invoke an ``int sisr_*`` entry; tensors are passed as device pointers; raises on error."""
     lib = load()
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(name, 1)
     rc = getattr(lib, name)(*[_conv(a) for a in args])
     if rc != 0:
         raise SisrError(f"{name}: {lib.sisr_last_error().decode()}")

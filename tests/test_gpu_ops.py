@@ -1,0 +1,279 @@
+"""GPU parity of every operator behind the C ABI against plain PyTorch fp32 on the CPU.
+bf16 storage / fp32 accumulate: relative L2 <= 1e-2 per tensor (north_star tolerance); kernels that
+are pure fp32 (spectral norm, Adam, losses, head) are held to 1e-4 .. 1e-5."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 1e-2
+
+
+def rel(a, b):
+    a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def nhwc(x):   # NCHW fp32 cpu -> NHWC bf16 cuda
+    return x.permute(0, 2, 3, 1).contiguous().to("cuda", torch.bfloat16)
+
+
+def nchw(x):   # NHWC (any dtype) cuda -> NCHW fp32 cpu
+    return x.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def bf(x):     # round an fp32 tensor to bf16 precision (reference sees the same inputs)
+    return x.to(torch.bfloat16).float()
+
+
+def test_layout_roundtrip(cuda):
+    from sisr_b200 import ops
+    for c in (3, 64, 512):
+        x = torch.randn(3, c, 6, 10)
+        y = ops.ToNHWC.apply(x.cuda())
+        assert y.shape == (3, 6, 10, c) and y.dtype == torch.bfloat16
+        assert torch.equal(nchw(y), bf(x))
+        z = ops.ToNCHW.apply(y)
+        assert torch.equal(z.cpu(), bf(x))
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, act, ps
+    (4, 24, 24, 64, 64, 3, 1, 1, "none", 0),      # G trunk (tensor cores)
+    (3, 12, 12, 64, 64, 3, 1, 1, "prelu", 0),     # M tail (432 rows)
+    (2, 12, 12, 64, 256, 3, 1, 1, "prelu", 2),    # upscale conv + PixelShuffle + PReLU
+    (4, 16, 16, 64, 64, 3, 2, 1, "none", 0),      # D stride-2
+    (4, 16, 16, 64, 128, 3, 1, 1, "none", 0),     # D widening
+    (2, 8, 8, 128, 256, 3, 2, 1, "none", 0),
+    (2, 6, 6, 256, 512, 3, 1, 1, "relu", 0),      # VGG deep layers
+    (2, 12, 12, 3, 64, 9, 1, 4, "prelu", 0),      # G first conv (CUDA cores)
+    (2, 16, 16, 3, 64, 3, 1, 1, "leaky", 0),      # D / VGG first conv (CUDA cores)
+    (2, 9, 7, 64, 64, 3, 1, 1, "none", 0),        # odd, non-square spatial size
+    (2, 9, 9, 64, 64, 3, 2, 1, "none", 0),        # stride 2 on odd size (CUDA-core dgrad)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_forward_backward(cuda, case):
+    from sisr_b200 import ops
+    n, h, w, cin, cout, k, stride, pad, act, ps = case
+    g = torch.Generator().manual_seed(hash(case) % 2**31)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g) * 0.1
+    slope = torch.tensor([0.25])
+    # reference (fp32, weights rounded to bf16 like the prepared copy)
+    xr = x.clone().requires_grad_(True)
+    wr = bf(wt).requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    sr = slope.clone().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, br, stride=stride, padding=pad)
+    if ps:
+        y_ref = F.pixel_shuffle(y_ref, 2)
+    y_ref = {"none": lambda t: t, "relu": torch.relu, "leaky": lambda t: F.leaky_relu(t, 0.01),
+             "prelu": lambda t: F.prelu(t, sr)}[act](y_ref)
+    gy = bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(gy)
+    # device
+    act_code = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "leaky": ops.ACT_LEAKY,
+                "prelu": ops.ACT_PRELU}[act]
+    xd = nhwc(x).requires_grad_(True)
+    wd = wt.cuda().requires_grad_(True)
+    bd = b.cuda().requires_grad_(True)
+    sd = slope.cuda().requires_grad_(True) if act == "prelu" else None
+    cfg = ops.ConvCfg(stride=stride, pad=pad, act=act_code, ps_r=ps, want_stats=(ps == 0))
+    y, stats = ops.Conv2dFn.apply(xd, wd, bd, None, None, sd, cfg)
+    assert rel(nchw(y), y_ref) < TOL_BF16
+    if stats is not None:
+        yy = nchw(y).double()
+        assert rel(stats[:cout], yy.sum(dim=(0, 2, 3))) < 1e-3 or float(yy.sum().abs()) < 1
+        assert rel(stats[cout:], (yy * yy).sum(dim=(0, 2, 3))) < 1e-3
+    y.backward(nhwc(gy))
+    torch.cuda.synchronize()
+    assert rel(nchw(xd.grad), xr.grad) < TOL_BF16
+    assert rel(wd.grad, wr.grad) < TOL_BF16
+    assert rel(bd.grad, br.grad) < TOL_BF16
+    if act == "prelu":
+        assert rel(sd.grad, sr.grad) < 2e-2
+
+
+def test_conv_tanh_nchw_output(cuda):
+    from sisr_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = bf(torch.randn(2, 64, 12, 12, generator=g))
+    wt = torch.randn(3, 64, 3, 3, generator=g) / 24
+    b = torch.randn(3, generator=g) * 0.1
+    xr, wr, br = x.clone().requires_grad_(True), bf(wt).requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = torch.tanh(F.conv2d(xr, wr, br, padding=1))
+    gy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(gy)
+    xd, wd, bd = nhwc(x).requires_grad_(True), wt.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y, _ = ops.Conv2dFn.apply(xd, wd, bd, None, None, None,
+                              ops.ConvCfg(act=ops.ACT_TANH, out_nchw_f32=True))
+    assert y.dtype == torch.float32 and y.shape == (2, 3, 12, 12)
+    assert rel(y, y_ref) < 1e-3
+    y.backward(gy.cuda())
+    assert rel(nchw(xd.grad), xr.grad) < TOL_BF16
+    assert rel(wd.grad, wr.grad) < TOL_BF16
+    assert rel(bd.grad, br.grad) < TOL_BF16
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_spectral_norm_conv(cuda, training):
+    """legacy spectral_norm semantics: one power iteration per training forward, in-place u/v,
+    gradient through sigma (reference: torch.nn.utils.spectral_norm on nn.Conv2d)."""
+    from torch.nn.utils import spectral_norm
+    from sisr_b200 import ops
+    torch.manual_seed(3)
+    ref = spectral_norm(torch.nn.Conv2d(64, 64, 3, padding=1))
+    ref.train(training)
+    w0, u0, v0 = ref.weight_orig.detach().clone(), ref.weight_u.clone(), ref.weight_v.clone()
+    x = bf(torch.randn(2, 64, 8, 8))
+    xr = x.clone().requires_grad_(True)
+    for _ in range(2):                       # two forwards: u/v must advance twice
+        y_ref = ref(xr)
+    gy = bf(torch.randn(y_ref.shape))
+    ref.zero_grad()
+    y_ref.backward(gy)
+    wd, bd = w0.cuda().requires_grad_(True), ref.bias.detach().cuda().requires_grad_(True)
+    ud, vd = u0.cuda(), v0.cuda()
+    xd = nhwc(x).requires_grad_(True)
+    cfg = ops.ConvCfg(training=training)
+    for _ in range(2):
+        y, _ = ops.Conv2dFn.apply(xd, wd, bd, ud, vd, None, cfg)
+    assert rel(ud, ref.weight_u) < 1e-4 and rel(vd, ref.weight_v) < 1e-4
+    assert rel(nchw(y), y_ref) < TOL_BF16
+    y.backward(nhwc(gy))
+    assert rel(wd.grad, ref.weight_orig.grad) < TOL_BF16
+    assert rel(nchw(xd.grad), xr.grad) < TOL_BF16
+
+
+@pytest.mark.parametrize("act", ["none", "prelu", "leaky"])
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_act(cuda, act, residual, training):
+    from sisr_b200 import ops
+    c = 64
+    g = torch.Generator().manual_seed(11)
+    y = bf(torch.randn(3, c, 10, 6, generator=g) * 2 + 0.5)
+    res = bf(torch.randn(3, c, 10, 6, generator=g))
+    bn = torch.nn.BatchNorm2d(c)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g)
+        bn.bias.uniform_(-0.5, 0.5, generator=g)
+        bn.running_mean.uniform_(-0.2, 0.2, generator=g)
+        bn.running_var.uniform_(0.8, 1.2, generator=g)
+    bn.train(training)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    slope = torch.tensor([0.25], requires_grad=True)
+    yr, rr = y.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    o = bn(yr)
+    o = {"none": lambda t: t, "leaky": lambda t: F.leaky_relu(t, 0.01),
+         "prelu": lambda t: F.prelu(t, slope)}[act](o)
+    if residual:
+        o = o + rr
+    go = bf(torch.randn(o.shape, generator=g))
+    o.backward(go)
+    code = {"none": ops.ACT_NONE, "leaky": ops.ACT_LEAKY, "prelu": ops.ACT_PRELU}[act]
+    yd, rd = nhwc(y).requires_grad_(True), nhwc(res).requires_grad_(True)
+    gam, bet = bn.weight.detach().cuda().requires_grad_(True), bn.bias.detach().cuda().requires_grad_(True)
+    rm, rv = rm0.cuda(), rv0.cuda()
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    sd = slope.detach().cuda().requires_grad_(True) if act == "prelu" else None
+    out = ops.BnActFn.apply(yd, None, gam, bet, rm, rv, nbt, rd if residual else None, sd,
+                            ops.BnCfg(act=code, training=training))
+    assert rel(nchw(out), o) < TOL_BF16
+    assert rel(rm, bn.running_mean) < 1e-4 and rel(rv, bn.running_var) < 1e-4
+    assert int(nbt) == (1 if training else 0)
+    out.backward(nhwc(go))
+    assert rel(nchw(yd.grad), yr.grad) < TOL_BF16
+    assert rel(gam.grad, bn.weight.grad) < TOL_BF16
+    assert rel(bet.grad, bn.bias.grad) < TOL_BF16
+    if residual:
+        assert rel(nchw(rd.grad), rr.grad) < TOL_BF16
+    if act == "prelu":
+        assert rel(sd.grad, slope.grad) < TOL_BF16
+
+
+def test_maxpool(cuda):
+    from sisr_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = bf(torch.relu(torch.randn(2, 64, 8, 12, generator=g)))   # many exact ties at 0
+    xr = x.clone().requires_grad_(True)
+    y_ref = F.max_pool2d(xr, 2, 2)
+    gy = bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(gy)
+    xd = nhwc(x).requires_grad_(True)
+    y = ops.MaxPool2Fn.apply(xd)
+    assert torch.equal(nchw(y), y_ref.detach())
+    y.backward(nhwc(gy))
+    assert torch.equal(nchw(xd.grad), xr.grad)
+
+
+def test_discriminator_head(cuda):
+    from sisr_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    n, h, w, c, mid = 5, 3, 3, 128, 256
+    x = bf(torch.randn(n, c, h, w, generator=g))
+    fc0 = torch.nn.Linear(c * h * w, mid)
+    fc2 = torch.nn.Linear(mid, 1)
+    xr = x.clone().requires_grad_(True)
+    p_ref = torch.sigmoid(fc2(F.leaky_relu(fc0(xr.reshape(n, -1)), 0.01)))
+    gp = torch.randn(n, 1, generator=g)
+    p_ref.backward(gp)
+    xd = nhwc(x).requires_grad_(True)
+    prm = [t.detach().cuda().requires_grad_(True) for t in (fc0.weight, fc0.bias, fc2.weight, fc2.bias)]
+    p = ops.DHeadFn.apply(xd, *prm)
+    assert p.shape == (n, 1)
+    assert rel(p, p_ref) < 1e-4
+    p.backward(gp.cuda())
+    assert rel(nchw(xd.grad), xr.grad) < TOL_BF16
+    for got, want in zip(prm, (fc0.weight, fc0.bias, fc2.weight, fc2.bias)):
+        assert rel(got.grad, want.grad) < 1e-4
+
+
+def test_losses(cuda):
+    from sisr_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    p = torch.rand(64, generator=g).clamp(1e-4, 1 - 1e-4)
+    p[0], p[1] = 1.0, 0.0                                   # saturated sigmoid: clamped logs
+    for t in (0.0, 0.9, 1.0):
+        pr = p.clone().requires_grad_(True)
+        l_ref = torch.nn.BCELoss()(pr, torch.full_like(pr, t))
+        (l_ref * 3).backward()
+        pd = p.cuda().requires_grad_(True)
+        l, mean_p = ops.bce_loss(pd, t)
+        (l * 3).backward()
+        assert abs(float(l) - float(l_ref)) < 1e-5 * max(1, abs(float(l_ref)))
+        assert abs(float(mean_p) - float(p.mean())) < 1e-5
+        assert rel(pd.grad[2:], pr.grad[2:]) < 1e-5
+    a, b = torch.randn(4, 1000, generator=g), torch.randn(4, 1000, generator=g)
+    ar, br2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    m_ref = torch.mean(torch.pow(ar - br2, 2))
+    (m_ref * 0.5).backward()
+    ad, bd = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    m = ops.mse_loss(ad, bd)
+    (m * 0.5).backward()
+    assert abs(float(m) - float(m_ref)) < 1e-5 * float(m_ref)
+    assert rel(ad.grad, ar.grad) < 1e-5 and rel(bd.grad, br2.grad) < 1e-5
+
+
+def test_fused_adam_matches_torch(cuda):
+    from sisr_b200.optim import Adam
+    torch.manual_seed(0)
+    shapes = [(64, 64, 3, 3), (64,), (1,), (1024, 300)] + [(7,)] * 30     # > one pointer table
+    ref_p = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    my_p = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref_p]
+    ref = torch.optim.Adam(ref_p, lr=1e-3, betas=(0.9, 0.999))
+    sched = torch.optim.lr_scheduler.LambdaLR(ref, lambda it: 0.9 ** it)
+    mine = Adam(my_p, lr=1e-3, betas=(0.9, 0.999), decay_per_step=0.9)
+    for _ in range(4):
+        for a, b in zip(ref_p, my_p):
+            gr = torch.randn_like(a)
+            a.grad, b.grad = gr, gr.cuda()
+        ref.step(); sched.step(); mine.step()
+    for a, b in zip(ref_p, my_p):
+        assert rel(b.detach(), a.detach()) < 1e-5

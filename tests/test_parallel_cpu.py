@@ -1,0 +1,63 @@
+"""CPU, world_size 2, gloo: the bucketed gradient all-reduce averages gradients across ranks and
+hands flat views to the optimizer; SyncBN statistic reduction goes through the same group."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import sisr_b200  # noqa: F401
+    from sisr_b200 import ops, parallel
+    r, _, w = parallel.init_distributed(backend="gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
+    parallel.broadcast_module(net)
+
+    class FakeOpt:
+        def __init__(self, params):
+            self.param_groups = [{"params": list(params)}]
+            self.grad_views, self.grad_scale = None, 1.0
+    opt = FakeOpt(net.parameters())
+    sync = parallel.GradSync(bucket_bytes=300)       # several buckets
+    sync.attach(opt)
+    torch.manual_seed(100 + rank)
+    x = torch.randn(5, 8)
+    net(x).pow(2).sum().backward()
+    sync.sync(opt)
+    local = [p.grad.clone() for p in net.parameters()]
+    summed = [opt.grad_views[p].clone() for p in net.parameters()]
+    gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
+    for g, out in zip(local, gathered):
+        dist.all_gather(out, g)
+    ok = all(torch.allclose(s, sum(o), atol=1e-6) for s, o in zip(summed, gathered))
+    ok = ok and abs(opt.grad_scale - 1.0 / world) < 1e-12
+    # SyncBN reduction helper
+    t = torch.full((4,), float(rank + 1))
+    ops._all_reduce(t)
+    ok = ok and ops._world() == world and torch.equal(t, torch.full((4,), 3.0))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_grad_sync_world2_gloo():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
