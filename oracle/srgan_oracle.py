@@ -67,6 +67,8 @@ class _RoundBF16(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
+        if _JITTER[0]:
+            x = x * (1 + _JITTER[0] * torch.randn(x.shape, generator=_JITTER[1]))
         return x.to(torch.bfloat16).float()
 
     @staticmethod
@@ -99,6 +101,25 @@ class _RoundFwdBF16(torch.autograd.Function):
 
 
 _EMULATE = [False]
+_JITTER = [0.0, None]
+
+
+class jitter_before_rounding:
+    """Inside ``emulate_bf16_storage``: multiply every activation by (1 + eps*N(0,1)) with eps at
+    fp32 round-off level *before* it is rounded to bf16.  Two such runs differ from each other by
+    exactly what two correct implementations with different fp32 summation orders (CPU vs tensor
+    cores) differ by; the tests use that run-to-run distance as the noise floor against which the
+    CUDA path's end-to-end gradients are judged."""
+
+    def __init__(self, eps: float = 1e-6, seed: int = 0):
+        self.eps, self.seed = eps, seed
+
+    def __enter__(self):
+        self.prev = list(_JITTER)
+        _JITTER[0], _JITTER[1] = self.eps, torch.Generator().manual_seed(self.seed)
+
+    def __exit__(self, *exc):
+        _JITTER[0], _JITTER[1] = self.prev
 
 
 class emulate_bf16_storage:

@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include "conv_simt.h"
+#include "conv_thin.h"
 #include "elementwise.h"
 #include "igemm.h"
 #include "linear.h"
@@ -45,6 +46,13 @@ bool desc_ok(const sisr_conv_desc* d) {
 bool tc_shape(const sisr_conv_desc* d) {
   return d->k == 3 && d->pad == 1 && (d->stride == 1 || d->stride == 2) && d->cin % 64 == 0 &&
          d->cout % 64 == 0 && (d->ps_r < 2 || (d->stride == 1 && (d->cout / 4) % 32 == 0));
+}
+// thin (3-channel) edge layers: stride 1, same-size
+bool thin_geometry(const sisr_conv_desc* d) {
+  return d->stride == 1 && d->oh == d->h && d->ow == d->w && d->ps_r < 2 && 2 * d->pad == d->k - 1;
+}
+ThinConv thin_of(const sisr_conv_desc* d, int cs, int cw) {
+  return ThinConv{d->n, d->h, d->w, cs, cw, d->k, d->pad};
 }
 SimtConv simt_of(const sisr_conv_desc* d) {
   return SimtConv{d->n, d->h, d->w, d->cin, d->oh, d->ow, d->cout, d->k, d->k, d->stride, d->pad};
@@ -124,6 +132,25 @@ int sisr_conv_fprop(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
     return 0;
   }
   if (d->ps_r == 2) return fail(1, "conv_fprop: PixelShuffle store needs a tensor-core shape");
+  if (thin_geometry(d) && d->cin == 3 && y && !y_nchw_f32 && act != SISR_ACT_TANH) {
+    const ThinConv t = thin_of(d, d->cin, d->cout);
+    if (thin_in_supported(t)) {
+      if (int rc = thin_in_conv(t, B(x), B(w), bias, act, slope, slope_ptr, 0, B(y), S(s)))
+        return fail(rc, "conv_fprop: %s", thin_last_error());
+      if (stats)
+        return wrap(col_stats(B(y), static_cast<long long>(d->n) * d->oh * d->ow, d->cout, stats, 1, S(s)),
+                    "col_stats");
+      return 0;
+    }
+  }
+  if (thin_geometry(d) && d->cout == 3 && !stats && act != SISR_ACT_PRELU) {
+    const ThinConv t = thin_of(d, d->cout, d->cin);
+    if (thin_out_supported(t)) {
+      if (int rc = thin_out_conv(t, B(x), B(w), bias, act, slope, 0, B(y), y_nchw_f32, S(s)))
+        return fail(rc, "conv_fprop: %s", thin_last_error());
+      return 0;
+    }
+  }
   if (int rc = conv_fprop_simt(simt_of(d), B(x), B(w), bias, act, slope, slope_ptr, B(y), y_nchw_f32,
                                S(s)))
     return wrap(rc, "conv_fprop_simt");
@@ -203,6 +230,22 @@ int sisr_conv_dgrad(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf1
     return 0;
   }
   if (d->ps_r == 2) return fail(1, "conv_dgrad: PixelShuffle layout needs a tensor-core shape");
+  if (thin_geometry(d) && w_dgrad && d->cout == 3) {      // dx (wide) from a 3-channel dy
+    const ThinConv t = thin_of(d, d->cout, d->cin);
+    if (thin_in_supported(t)) {
+      if (int rc = thin_in_conv(t, B(dy), B(w_dgrad), nullptr, ACT_NONE, 0.f, nullptr, 1, B(dx), S(s)))
+        return fail(rc, "conv_dgrad: %s", thin_last_error());
+      return 0;
+    }
+  }
+  if (thin_geometry(d) && w_dgrad && d->cin == 3) {       // 3-channel dx from a wide dy
+    const ThinConv t = thin_of(d, d->cin, d->cout);
+    if (thin_out_supported(t)) {
+      if (int rc = thin_out_conv(t, B(dy), B(w_dgrad), nullptr, ACT_NONE, 0.f, 1, B(dx), nullptr, S(s)))
+        return fail(rc, "conv_dgrad: %s", thin_last_error());
+      return 0;
+    }
+  }
   return wrap(conv_dgrad_simt(simt_of(d), B(dy), B(w_fprop), B(dx), S(s)), "conv_dgrad_simt");
 }
 
@@ -220,6 +263,28 @@ int sisr_conv_wgrad(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
                                  d->ow, d->cout, d->stride, d->ps_r, S(s)))
       return fail(rc, "conv_wgrad: %s", wgrad_tc_last_error());
     return 0;
+  }
+  if (thin_geometry(d) && d->cin == 3) {                  // thin-in conv: small = x, wide = dy
+    const ThinConv t = thin_of(d, d->cin, d->cout);
+    if (thin_wgrad_supported(t)) {
+      if (int rc = thin_wgrad(t, B(x), B(dy), +1, gp, nullptr, S(s)))
+        return fail(rc, "conv_wgrad: %s", thin_last_error());
+      if (dbias_perm) {
+        cudaMemsetAsync(dbias_perm, 0, sizeof(float) * d->cout, S(s));
+        return wrap(col_stats(B(dy), static_cast<long long>(d->n) * d->oh * d->ow, d->cout, dbias_perm, 0,
+                              S(s)),
+                    "col_stats");
+      }
+      return 0;
+    }
+  }
+  if (thin_geometry(d) && d->cout == 3) {                 // thin-out conv: small = dy, wide = x
+    const ThinConv t = thin_of(d, d->cout, d->cin);
+    if (thin_wgrad_supported(t)) {
+      if (int rc = thin_wgrad(t, B(dy), B(x), -1, gp, dbias_perm, S(s)))
+        return fail(rc, "conv_wgrad: %s", thin_last_error());
+      return 0;
+    }
   }
   return wrap(conv_wgrad_simt(simt_of(d), B(x), B(dy), gp, dbias_perm, d->ps_r == 2 ? d->cout / 4 : 0, 0,
                               S(s)),
