@@ -63,17 +63,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([s.strip() for s in line.split(",")])
+            self.samples.append((time.time(), [s.strip() for s in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in the wall-clock window [t0, t1] (the timed regions)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        rows = [s for (t, s) in self.samples if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.2)]
+        sm = sorted(int(s[0]) for s in rows if s and s[0].isdigit())
+        mx = [int(s[1]) for (_, s) in self.samples if len(s) > 1 and s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 6
+        reasons = sorted({names[i] for s in rows if len(s) >= 6
                           for i in range(4) if s[2 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
@@ -146,16 +148,17 @@ def build_trainer(dev, batch, world, grad_sync=None):
     return tr
 
 
-def time_dominant_kernel(dev, batch, iters=20):
-    """CUDA-event timing of the tcgen05 implicit-GEMM conv on the layer with the largest FLOP share
-    of the step (VGG conv3_x: 256->256 at 24x24), launched alone through the C ABI."""
+def time_conv_kernel(dev, n, h, cin, cout, with_stats, iters=20):
+    """CUDA-event timing of one tcgen05 implicit-GEMM conv launch through the C ABI, L2 flushed
+    (a 256 MB write) before every launch."""
     import torch
     from sisr_b200 import _lib
-    n, h, w, cin, cout = batch, 24, 24, 256, 256
+    w = h
     x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
     wt = (torch.randn(cout, 3, 3, cin, device=dev) * 0.02).to(torch.bfloat16)
     bias = torch.zeros(cout, device=dev)
     y = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+    stats = torch.empty(2 * cout, device=dev) if with_stats else None
     d = _lib.ConvDesc(n, h, w, cin, h, w, cout, 3, 1, 1, 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
@@ -164,15 +167,22 @@ def time_dominant_kernel(dev, batch, iters=20):
         flush.zero_()                                  # evict L2 (126 MB) between launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.call("sisr_conv_fprop", d, x, wt, bias, 1, 0.0, None, y, None, None, st)
+        _lib.call("sisr_conv_fprop", d, x, wt, bias, 0, 0.0, None, y, None, stats, st)
         e1.record()
         e1.synchronize()
         if i >= 3:
             ms.append(e0.elapsed_time(e1))
     flops = 2.0 * n * h * w * cout * 9 * cin
     avg = sum(ms) / len(ms)
-    return {"kernel": "igemm_tc_kernel<256,4> (conv3x3 256->256 @24x24, batch %d)" % n,
+    return {"kernel": "igemm_tc_kernel conv3x3 %d->%d @%dx%d batch %d%s" %
+                      (cin, cout, h, w, n, " +BN stats" if with_stats else ""),
             "flops": flops, "ms": avg, "tflops": flops / (avg * 1e-3) / 1e12}
+
+
+def time_dominant_kernel(dev, batch):
+    """The kernel with the largest share of the step (profiles/: igemm_tc_kernel<64,4>, 18 %) on its
+    most frequent shape: the generator trunk conv 64->64 @24x24 with fused BN statistics."""
+    return time_conv_kernel(dev, batch, 24, 64, 64, True)
 
 
 def run_ours(args):
@@ -183,6 +193,9 @@ def run_ours(args):
     from oracle import state_factory as S   # synthetic patch recipe only (host side)
 
     rank, local, world = parallel.init_distributed()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs ~1 s to start; samples are windowed later
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     batch = args.batch
@@ -213,9 +226,6 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     # ---- timed region 1: device-resident inputs (inputs > L2? no: 126 MB L2 is flushed by the step
     # itself: one step touches > 1 GB of activations and weights)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,6 +234,7 @@ def run_ours(args):
     barrier()
     if os.environ.get("SISR_PROFILE_TIMED_REGION"):      # ncu --profile-from-start off
         torch.cuda.profiler.start()
+    wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         out = step()
@@ -256,13 +267,15 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.barrier()
         return
     peaks = measured_peaks()
     dom = time_dominant_kernel(dev, batch)
+    others = [time_conv_kernel(dev, batch, 24, 256, 256, False), time_conv_kernel(dev, batch, 48, 128, 128, False),
+              time_conv_kernel(dev, batch, 12, 512, 512, False)]
     total_patches = batch * world * args.steps
     value = total_patches / (ms * 1e-3)
     line = {
@@ -288,7 +301,10 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_burst"],
                      "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["bf16_burst"], "traffic": None,
                      "kernel": dom["kernel"], "ms_per_launch": dom["ms"], "peak_source": peaks["source"],
+                     "share_of_step": "igemm_tc_kernel<64,4> = 18 % of step time (profiles/r1_step_launches_b64_eager.csv)",
                      "l2_flushed_between_launches": True},
+        "roofline_other": [{"kernel": o["kernel"], "achieved": o["tflops"], "unit": "TFLOP/s",
+                            "frac": o["tflops"] / peaks["bf16_burst"], "ms_per_launch": o["ms"]} for o in others],
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -304,7 +320,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)

@@ -58,6 +58,16 @@ int sisr_tanh_bwd_nchw_to_nhwc(const float* dout, const float* y, sisr_bf16* dpr
 size_t sisr_sn_workspace_floats(int cout, int k);
 int sisr_sn_power_iteration(const float* w_orig, float* u, float* v, float* sigma, int cout, int k,
                             int training, float eps, float* workspace, void* stream);
+/* Batched variants: one launch chain for every conv of a network.  `table` is a DEVICE array of
+ * n_layers records {w, u, v, t, s, sigma, u_saved, v_saved : pointers; cout, K, training, pad : int}
+ * (sn) / {w, sigma, bias, w_fprop, w_dgrad, bias_perm : pointers; cout, cin, k, ps_r : int} (prep);
+ * *_begin are DEVICE int arrays with the first block (or row) of each layer: wtu blocks cover 128
+ * weight columns, prep blocks cover 1024 weight elements. */
+int sisr_sn_power_iteration_batched(const void* table, const int* wtu_begin, const int* row_begin,
+                                    int n_layers, int total_wtu_blocks, int total_rows, float eps,
+                                    void* stream);
+int sisr_weight_prep_batched(const void* table, const int* blk_begin, int n_layers, int total_blocks,
+                             void* stream);
 /* w: [cout,cin,k,k] fp32 -> w_fprop: [cout',k,k,cin] bf16, w_dgrad: [cin,k,k,cout'] bf16 (nullable),
  * both scaled by 1/sigma (sigma nullable); bias_perm (nullable) = bias in the permuted row order. */
 int sisr_weight_prep(const float* w, const float* sigma, const float* bias, sisr_bf16* w_fprop,

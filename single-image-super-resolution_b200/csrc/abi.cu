@@ -88,6 +88,19 @@ int sisr_sn_power_iteration(const float* w, float* u, float* v, float* sigma, in
   return wrap(sn_power_iteration(w, u, v, sigma, cout, k, training, eps, ws, S(s)),
               "sn_power_iteration");
 }
+int sisr_sn_power_iteration_batched(const void* table, const int* wtu_begin, const int* row_begin,
+                                    int n_layers, int total_wtu_blocks, int total_rows, float eps,
+                                    void* s) {
+  return wrap(sn_power_iteration_batched(static_cast<const SnLayer*>(table), wtu_begin, row_begin,
+                                         n_layers, total_wtu_blocks, total_rows, eps, S(s)),
+              "sn_power_iteration_batched");
+}
+int sisr_weight_prep_batched(const void* table, const int* blk_begin, int n_layers, int total_blocks,
+                             void* s) {
+  return wrap(weight_prep_batched(static_cast<const PrepLayer*>(table), blk_begin, n_layers,
+                                  total_blocks, S(s)),
+              "weight_prep_batched");
+}
 int sisr_weight_prep(const float* w, const float* sigma, const float* bias, sisr_bf16* wf, sisr_bf16* wd,
                      float* bias_perm, int cout, int cin, int k, int ps_r, void* s) {
   return wrap(weight_prep(w, sigma, bias, B(wf), B(wd), bias_perm, cout, cin, k, k, ps_r, S(s)),

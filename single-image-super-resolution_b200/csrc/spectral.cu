@@ -141,6 +141,113 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ gp, const float* _
   }
 }
 
+// ------------------------------------------------------------------ batched (table-driven) variants
+// One launch covers every spectral-normed conv of a network.  The table lives in device memory.
+__device__ __forceinline__ int find_layer(const int* __restrict__ begin, int n, int b) {
+  int lo = 0, hi = n - 1;       // begin[l] <= b < begin[l+1]
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (begin[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// t[k] = sum_co W[co,k] u[co] for a 128-column chunk of one layer (training layers only)
+__global__ void __launch_bounds__(256)
+sn_batched_wtu_kernel(const SnLayer* __restrict__ tab, const int* __restrict__ blk_begin, int n_layers) {
+  __shared__ float part[128];
+  const int l = find_layer(blk_begin, n_layers, blockIdx.x);
+  const SnLayer L = tab[l];
+  if (!L.training) return;
+  const int k = (blockIdx.x - blk_begin[l]) * 128 + (threadIdx.x & 127);
+  const int half = threadIdx.x >> 7;
+  float acc = 0.f;
+  if (k < L.K) {
+    const int c0 = half ? L.cout / 2 : 0, c1 = half ? L.cout : L.cout / 2;
+    for (int co = c0; co < c1; ++co) acc = fmaf(L.w[static_cast<size_t>(co) * L.K + k], L.u[co], acc);
+  }
+  if (half) part[threadIdx.x & 127] = acc;
+  __syncthreads();
+  if (!half && k < L.K) L.t[k] = acc + part[threadIdx.x];
+}
+// s_raw[co] = sum_k W[co,k] * (training ? t[k] : v[k]); one block per (layer, row)
+__global__ void __launch_bounds__(128)
+sn_batched_wv_kernel(const SnLayer* __restrict__ tab, const int* __restrict__ row_begin, int n_layers) {
+  __shared__ float scratch[32];
+  const int l = find_layer(row_begin, n_layers, blockIdx.x);
+  const SnLayer L = tab[l];
+  const int co = blockIdx.x - row_begin[l];
+  const float* vec = L.training ? L.t : L.v;
+  const float* wr = L.w + static_cast<size_t>(co) * L.K;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < L.K; k += blockDim.x) acc = fmaf(wr[k], vec[k], acc);
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) L.s[co] = acc;
+}
+// per layer: normalise, write u/v (training), sigma, and the copies kept for backward
+__global__ void __launch_bounds__(256)
+sn_batched_finish_kernel(const SnLayer* __restrict__ tab, float eps) {
+  __shared__ float scratch[32];
+  const SnLayer L = tab[blockIdx.x];
+  if (L.training) {
+    float a = 0.f;
+    for (int k = threadIdx.x; k < L.K; k += blockDim.x) a += L.t[k] * L.t[k];
+    const float nt = fmaxf(sqrtf(block_sum(a, scratch)), eps);
+    for (int k = threadIdx.x; k < L.K; k += blockDim.x) {
+      const float vv = L.t[k] / nt;
+      L.v[k] = vv;
+      L.v_saved[k] = vv;
+    }
+    float b = 0.f;
+    for (int c = threadIdx.x; c < L.cout; c += blockDim.x) {
+      const float sv = L.s[c] / nt;
+      b += sv * sv;
+    }
+    const float ss = block_sum(b, scratch);
+    const float ns = fmaxf(sqrtf(ss), eps);
+    for (int c = threadIdx.x; c < L.cout; c += blockDim.x) {
+      const float uu = (L.s[c] / nt) / ns;
+      L.u[c] = uu;
+      L.u_saved[c] = uu;
+    }
+    if (threadIdx.x == 0) *L.sigma = ss / ns;
+  } else {
+    float b = 0.f;
+    for (int c = threadIdx.x; c < L.cout; c += blockDim.x) {
+      b += L.u[c] * L.s[c];
+      L.u_saved[c] = L.u[c];
+    }
+    for (int k = threadIdx.x; k < L.K; k += blockDim.x) L.v_saved[k] = L.v[k];
+    b = block_sum(b, scratch);
+    if (threadIdx.x == 0) *L.sigma = b;
+  }
+}
+
+// weight_prep for every conv of a network; block -> (layer, chunk of 1024 elements)
+__global__ void __launch_bounds__(256)
+weight_prep_batched_kernel(const PrepLayer* __restrict__ tab, const int* __restrict__ blk_begin,
+                           int n_layers) {
+  const int l = find_layer(blk_begin, n_layers, blockIdx.x);
+  const PrepLayer L = tab[l];
+  const float inv = L.sigma ? 1.f / *L.sigma : 1.f;
+  const int taps = L.k * L.k;
+  const long long total = static_cast<long long>(L.cout) * taps * L.cin;
+  const long long base = static_cast<long long>(blockIdx.x - blk_begin[l]) * 1024;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long i = base + j * 256 + threadIdx.x;
+    if (i >= total) break;
+    const int ci = static_cast<int>(i % L.cin);
+    const int tap = static_cast<int>((i / L.cin) % taps);
+    const int cop = static_cast<int>(i / (static_cast<long long>(L.cin) * taps));
+    const int co = unpermute_row(cop, L.cout, L.ps_r);
+    const __nv_bfloat16 h = __float2bfloat16_rn(L.w[(static_cast<size_t>(co) * L.cin + ci) * taps + tap] * inv);
+    L.wf[i] = h;
+    if (L.wd) L.wd[(static_cast<size_t>(ci) * taps + tap) * L.cout + cop] = h;
+    if (L.bias_perm && tap == 0 && ci == 0) L.bias_perm[cop] = L.bias[co];
+  }
+}
+
 inline int grid_for(long long work) {
   long long b = (work + kThreads - 1) / kThreads;
   if (b > 148 * 8) b = 148 * 8;
@@ -166,6 +273,24 @@ int sn_power_iteration(const float* w, float* u, float* v, float* sigma, int Cou
     sn_wv_kernel<<<Cout, kThreads, 0, s>>>(w, v, s_raw, K);
   }
   sn_finish_kernel<<<1, kThreads, 0, s>>>(t, s_raw, u, v, sigma, Cout, K, training, eps);
+  return check();
+}
+
+int sn_power_iteration_batched(const SnLayer* tab_dev, const int* wtu_begin_dev, const int* row_begin_dev,
+                               int n_layers, int total_wtu_blocks, int total_rows, float eps,
+                               cudaStream_t s) {
+  if (n_layers == 0) return 0;
+  if (total_wtu_blocks > 0)
+    sn_batched_wtu_kernel<<<total_wtu_blocks, 256, 0, s>>>(tab_dev, wtu_begin_dev, n_layers);
+  sn_batched_wv_kernel<<<total_rows, 128, 0, s>>>(tab_dev, row_begin_dev, n_layers);
+  sn_batched_finish_kernel<<<n_layers, 256, 0, s>>>(tab_dev, eps);
+  return check();
+}
+
+int weight_prep_batched(const PrepLayer* tab_dev, const int* blk_begin_dev, int n_layers,
+                        int total_blocks, cudaStream_t s) {
+  if (n_layers == 0 || total_blocks == 0) return 0;
+  weight_prep_batched_kernel<<<total_blocks, 256, 0, s>>>(tab_dev, blk_begin_dev, n_layers);
   return check();
 }
 

@@ -6,7 +6,34 @@
 
 namespace sisr {
 
+// Device-resident per-layer descriptors of the batched (one launch per network) variants.
+struct SnLayer {
+  const float* w;      // [cout, K] fp32 master weight
+  float* u;            // [cout]  module buffer (updated in training)
+  float* v;            // [K]
+  float* t;            // [K]     scratch
+  float* s;            // [cout]  scratch
+  float* sigma;        // [1]
+  float* u_saved;      // [cout]  copy used by the backward pass of this forward call
+  float* v_saved;      // [K]
+  int cout, K, training, pad_;
+};
+struct PrepLayer {
+  const float* w;
+  const float* sigma;      // nullable
+  const float* bias;       // nullable unless bias_perm
+  __nv_bfloat16* wf;
+  __nv_bfloat16* wd;       // nullable
+  float* bias_perm;        // nullable
+  int cout, cin, k, ps_r;
+};
+
 size_t sn_workspace_floats(int Cout, int K);
+int sn_power_iteration_batched(const SnLayer* tab_dev, const int* wtu_begin_dev, const int* row_begin_dev,
+                               int n_layers, int total_wtu_blocks, int total_rows, float eps,
+                               cudaStream_t s);
+int weight_prep_batched(const PrepLayer* tab_dev, const int* blk_begin_dev, int n_layers,
+                        int total_blocks, cudaStream_t s);
 // w: [Cout, K] fp32 (K = Cin*kh*kw, native flatten order).  training: one power iteration,
 // u/v updated in place, sigma written.  eval: sigma = u^T W v with the stored vectors.
 int sn_power_iteration(const float* w, float* u, float* v, float* sigma, int Cout, int K,
