@@ -58,16 +58,26 @@ int sisr_tanh_bwd_nchw_to_nhwc(const float* dout, const float* y, sisr_bf16* dpr
 size_t sisr_sn_workspace_floats(int cout, int k);
 int sisr_sn_power_iteration(const float* w_orig, float* u, float* v, float* sigma, int cout, int k,
                             int training, float eps, float* workspace, void* stream);
-/* Batched variants: one launch chain for every conv of a network.  `table` is a DEVICE array of
- * n_layers records {w, u, v, t, s, sigma, u_saved, v_saved : pointers; cout, K, training, pad : int}
- * (sn) / {w, sigma, bias, w_fprop, w_dgrad, bias_perm : pointers; cout, cin, k, ps_r : int} (prep);
- * *_begin are DEVICE int arrays with the first block (or row) of each layer: wtu blocks cover 128
- * weight columns, prep blocks cover 1024 weight elements. */
-int sisr_sn_power_iteration_batched(const void* table, const int* wtu_begin, const int* row_begin,
-                                    int n_layers, int total_wtu_blocks, int total_rows, float eps,
-                                    void* stream);
-int sisr_weight_prep_batched(const void* table, const int* blk_begin, int n_layers, int total_blocks,
-                             void* stream);
+/* Batched variants: one launch chain for every conv of a network (37 layers in G, 8 in D).  `layers`
+ * is a HOST array; the pointers inside are DEVICE pointers.  t [k] and s [cout] are scratch;
+ * u_saved / v_saved receive the vectors this call's sigma was computed with (for the backward pass).
+ * training = 0: no iteration, sigma = u^T W v with the stored vectors. */
+typedef struct sisr_sn_layer {
+  const float* w;
+  float *u, *v, *t, *s, *sigma, *u_saved, *v_saved;
+  int cout, k, training, reserved;
+} sisr_sn_layer;
+typedef struct sisr_prep_layer {
+  const float* w;
+  const float* sigma;      /* nullable */
+  const float* bias;       /* nullable unless bias_perm */
+  sisr_bf16* w_fprop;
+  sisr_bf16* w_dgrad;      /* nullable */
+  float* bias_perm;        /* nullable */
+  int cout, cin, k, ps_r;
+} sisr_prep_layer;
+int sisr_sn_power_iteration_batched(const sisr_sn_layer* layers, int n_layers, float eps, void* stream);
+int sisr_weight_prep_batched(const sisr_prep_layer* layers, int n_layers, void* stream);
 /* w: [cout,cin,k,k] fp32 -> w_fprop: [cout',k,k,cin] bf16, w_dgrad: [cin,k,k,cout'] bf16 (nullable),
  * both scaled by 1/sigma (sigma nullable); bias_perm (nullable) = bias in the permuted row order. */
 int sisr_weight_prep(const float* w, const float* sigma, const float* bias, sisr_bf16* w_fprop,
@@ -112,14 +122,17 @@ int sisr_bn_apply(const sisr_bf16* y, const float* scale, const float* shift, in
 int sisr_bn_bwd_reduce(const sisr_bf16* dout, const sisr_bf16* y, const float* mean, const float* invstd,
                        const float* scale, const float* shift, int act, float slope,
                        const float* slope_ptr, float* sums, long long rows, int c, void* stream);
+/* colsum (nullable, fp32 [c], accumulated - caller zeroes): per-channel sum of the dy written, i.e. the
+ * bias gradient of the conv that feeds this BatchNorm */
 int sisr_bn_bwd_apply(const sisr_bf16* dout, const sisr_bf16* y, const float* mean, const float* invstd,
                       const float* scale, const float* shift, int act, float slope,
                       const float* slope_ptr, const float* sums, float count, sisr_bf16* dy,
-                      long long rows, int c, void* stream);
-/* backward of an activation fused in a conv epilogue, from its OUTPUT (needs slope > 0):
- * din = dout * f'(out); dslope (nullable, accumulated) += sum dout * min(0, pre) */
+                      float* colsum, long long rows, int c, void* stream);
+/* backward of an activation fused in a conv epilogue, from its OUTPUT (needs slope > 0), on [rows, c]:
+ * din = dout * f'(out); dslope (nullable, accumulated) += sum dout * min(0, pre);
+ * colsum (nullable, fp32 [c], accumulated): per-channel sum of din (the conv's bias gradient) */
 int sisr_act_bwd(const sisr_bf16* dout, const sisr_bf16* out, int act, float slope, const float* slope_ptr,
-                 sisr_bf16* din, float* dslope, long long numel, void* stream);
+                 sisr_bf16* din, float* dslope, float* colsum, long long rows, int c, void* stream);
 
 /* ---- MaxPool2d(2,2) of torchvision vgg19.features ---- */
 int sisr_maxpool2_fwd(const sisr_bf16* x, sisr_bf16* y, int n, int h, int w, int c, void* stream);

@@ -88,17 +88,16 @@ int sisr_sn_power_iteration(const float* w, float* u, float* v, float* sigma, in
   return wrap(sn_power_iteration(w, u, v, sigma, cout, k, training, eps, ws, S(s)),
               "sn_power_iteration");
 }
-int sisr_sn_power_iteration_batched(const void* table, const int* wtu_begin, const int* row_begin,
-                                    int n_layers, int total_wtu_blocks, int total_rows, float eps,
-                                    void* s) {
-  return wrap(sn_power_iteration_batched(static_cast<const SnLayer*>(table), wtu_begin, row_begin,
-                                         n_layers, total_wtu_blocks, total_rows, eps, S(s)),
+static_assert(sizeof(sisr_sn_layer) == sizeof(SnLayer), "sisr_sn_layer layout");
+static_assert(sizeof(sisr_prep_layer) == sizeof(PrepLayer), "sisr_prep_layer layout");
+int sisr_sn_power_iteration_batched(const sisr_sn_layer* layers, int n_layers, float eps, void* s) {
+  if (n_layers < 0 || (n_layers > 0 && !layers)) return fail(1, "sn_power_iteration_batched: bad arguments");
+  return wrap(sn_power_iteration_batched(reinterpret_cast<const SnLayer*>(layers), n_layers, eps, S(s)),
               "sn_power_iteration_batched");
 }
-int sisr_weight_prep_batched(const void* table, const int* blk_begin, int n_layers, int total_blocks,
-                             void* s) {
-  return wrap(weight_prep_batched(static_cast<const PrepLayer*>(table), blk_begin, n_layers,
-                                  total_blocks, S(s)),
+int sisr_weight_prep_batched(const sisr_prep_layer* layers, int n_layers, void* s) {
+  if (n_layers < 0 || (n_layers > 0 && !layers)) return fail(1, "weight_prep_batched: bad arguments");
+  return wrap(weight_prep_batched(reinterpret_cast<const PrepLayer*>(layers), n_layers, S(s)),
               "weight_prep_batched");
 }
 int sisr_weight_prep(const float* w, const float* sigma, const float* bias, sisr_bf16* wf, sisr_bf16* wd,
@@ -280,21 +279,15 @@ int sisr_conv_wgrad(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
   if (thin_geometry(d) && d->cin == 3) {                  // thin-in conv: small = x, wide = dy
     const ThinConv t = thin_of(d, d->cin, d->cout);
     if (thin_wgrad_supported(t)) {
-      if (int rc = thin_wgrad(t, B(x), B(dy), +1, gp, nullptr, S(s)))
+      if (int rc = thin_wgrad(t, B(x), B(dy), +1, gp, nullptr, dbias_perm, S(s)))
         return fail(rc, "conv_wgrad: %s", thin_last_error());
-      if (dbias_perm) {
-        cudaMemsetAsync(dbias_perm, 0, sizeof(float) * d->cout, S(s));
-        return wrap(col_stats(B(dy), static_cast<long long>(d->n) * d->oh * d->ow, d->cout, dbias_perm, 0,
-                              S(s)),
-                    "col_stats");
-      }
       return 0;
     }
   }
   if (thin_geometry(d) && d->cout == 3) {                 // thin-out conv: small = dy, wide = x
     const ThinConv t = thin_of(d, d->cout, d->cin);
     if (thin_wgrad_supported(t)) {
-      if (int rc = thin_wgrad(t, B(dy), B(x), -1, gp, dbias_perm, S(s)))
+      if (int rc = thin_wgrad(t, B(dy), B(x), -1, gp, dbias_perm, nullptr, S(s)))
         return fail(rc, "conv_wgrad: %s", thin_last_error());
       return 0;
     }
@@ -333,14 +326,15 @@ int sisr_bn_bwd_reduce(const sisr_bf16* dout, const sisr_bf16* y, const float* m
 int sisr_bn_bwd_apply(const sisr_bf16* dout, const sisr_bf16* y, const float* mean, const float* invstd,
                       const float* scale, const float* shift, int act, float slope,
                       const float* slope_ptr, const float* sums, float count, sisr_bf16* dy,
-                      long long rows, int c, void* s) {
+                      float* colsum, long long rows, int c, void* s) {
   return wrap(bn_bwd_apply(B(dout), B(y), mean, invstd, scale, shift, act, slope, slope_ptr, sums, count,
-                           B(dy), rows, c, S(s)),
+                           B(dy), colsum, rows, c, S(s)),
               "bn_bwd_apply");
 }
 int sisr_act_bwd(const sisr_bf16* dout, const sisr_bf16* out, int act, float slope, const float* slope_ptr,
-                 sisr_bf16* din, float* dslope, long long numel, void* s) {
-  return wrap(act_bwd(B(dout), B(out), act, slope, slope_ptr, B(din), dslope, numel, S(s)), "act_bwd");
+                 sisr_bf16* din, float* dslope, float* colsum, long long rows, int c, void* s) {
+  return wrap(act_bwd(B(dout), B(out), act, slope, slope_ptr, B(din), dslope, colsum, rows, c, S(s)),
+              "act_bwd");
 }
 int sisr_maxpool2_fwd(const sisr_bf16* x, sisr_bf16* y, int n, int h, int w, int c, void* s) {
   return wrap(maxpool2_fwd(B(x), B(y), n, h, w, c, S(s)), "maxpool2_fwd");

@@ -1,10 +1,13 @@
-// CUDA-core kernels for the "thin" edge layers of the SRGAN step, where one side of the
-// convolution has 3 channels (RGB) and tensor-core tiles would be > 90 % padding:
-//   thin-in  : C_small -> C_wide  (G first conv 9x9, D / VGG first conv 3x3, dgrad of the G output conv)
-//   thin-out : C_wide  -> C_small (G output conv 3x3 + Tanh, dgrad of the D / VGG first conv)
+// Kernels for the "thin" edge layers of the SRGAN step, where one side of the convolution has
+// 3 channels (RGB):
+//   thin-in   : 3 -> CW   (G first conv 9x9, D / VGG first conv 3x3, dgrad of the G output conv)
+//   thin-out  : CW -> 3   (G output conv 3x3 + Tanh, dgrad of the D / VGG first conv)
 //   thin-wgrad: correlation of a 3-channel tensor with a wide tensor over the k x k taps
-// Stride 1 only.  NHWC bf16 activations, fp32 accumulate, weights staged in shared memory as fp32.
-// These layers are < 2 % of the step's FLOPs; the goal is to keep them near their memory floor.
+// Stride 1, same-size.  These layers are < 2 % of the step's FLOPs but stream the largest
+// activations of the step (B x 96 x 96 x 64), so they are HBM-bound: each kernel stages its tile in
+// shared memory with 16-byte accesses and contracts it with warp-level mma.sync (m16n8k16, bf16
+// inputs, fp32 accumulate) -- a tcgen05 tile (N >= 16, K = 64 per swizzle atom) would be > 80 %
+// padding on a K = 27 or N = 3 problem.
 #include "conv_thin.h"
 
 #include <stdio.h>
@@ -21,215 +24,355 @@ __device__ __forceinline__ float act_apply(float x, int act, float slope) {
   return x > 0.f ? x : x * slope;
 }
 
-// ------------------------------------------------------------------ thin-in: CS -> CW, k x k
-// w: [CW][k*k][CS] bf16 (prepared layout); flip: use tap (k*k-1-t) (transposed conv)
-template <int CS>
-__global__ void __launch_bounds__(128)
-thin_in_kernel(ThinConv c, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-               const float* __restrict__ bias, int act, float slope, const float* __restrict__ slope_ptr,
-               int flip, __nv_bfloat16* __restrict__ y) {
-  extern __shared__ float s_w[];  // [(tap*CS + cs)][CW]
-  const int T = c.k * c.k;
-  for (int i = threadIdx.x; i < c.CW * T * CS; i += blockDim.x) {
-    const int cs = i % CS, tap = (i / CS) % T, cw = i / (CS * T);
-    const int tt = flip ? T - 1 - tap : tap;
-    s_w[(tt * CS + cs) * c.CW + cw] = __bfloat162float(w[i]);
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                              uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+// D(16x8, fp32) += A(16x16, row) * B(16x8, col), bf16 inputs
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr int kThreads = 256;
+constexpr int kTileQ = 128;    // pixels per tile (thin-in, wgrad)
+constexpr int kLdC = 72;       // bf16 row stride of a staged [pixels][64 channels] tile (144 B)
+
+// ------------------------------------------------------------------ thin-in: 3 -> 64, k x k
+// GEMM per 128-pixel tile: Y[128, 64] = Xim[128, KP] * W[64, KP]^T, KP = k*k*3 zero-padded.
+// w: [CW][k*k][3] bf16; flip: the tap at position t uses w[.][k*k-1-t][.] (transposed conv).
+template <int KP>
+__global__ void __launch_bounds__(kThreads)
+thin_in_mma_kernel(ThinConv c, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                   const float* __restrict__ bias, int act, float slope,
+                   const float* __restrict__ slope_ptr, int flip, __nv_bfloat16* __restrict__ y) {
+  constexpr int LDK = KP + 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [64][LDK]
+  __nv_bfloat16* Xs = Ws + 64 * LDK;                                // [128][LDK]
+  __nv_bfloat16* Cs = Xs + kTileQ * LDK;                            // [128][kLdC]
+  const int T = c.k * c.k, KT = T * 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cwb = blockIdx.y * 64;
+  const long long npix = static_cast<long long>(c.N) * c.H * c.W;
+  const long long q0 = static_cast<long long>(blockIdx.x) * kTileQ;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+
+  for (int i = tid; i < 64 * LDK; i += kThreads) {
+    const int cw = i / LDK, j = i - cw * LDK;
+    __nv_bfloat16 v = zero;
+    if (j < KT) {
+      const int tap = j / 3, cs = j - tap * 3;
+      const int st = flip ? T - 1 - tap : tap;
+      v = w[(static_cast<size_t>(cwb + cw) * T + st) * 3 + cs];
+    }
+    Ws[i] = v;
+  }
+  {  // im2col of the tile: two threads per pixel, alternating taps
+    const int ql = tid >> 1, half = tid & 1;
+    const long long q = q0 + ql;
+    const bool valid = q < npix;
+    const long long qq = valid ? q : 0;
+    const int ow = static_cast<int>(qq % c.W);
+    const int oh = static_cast<int>((qq / c.W) % c.H);
+    const __nv_bfloat16* xim = x + (qq - (static_cast<long long>(oh) * c.W + ow)) * 3;
+    __nv_bfloat16* row = Xs + ql * LDK;
+    for (int tap = half; tap < T; tap += 2) {
+      const int kh = tap / c.k, kw = tap - kh * c.k;
+      const int ih = oh - c.pad + kh, iw = ow - c.pad + kw;
+      __nv_bfloat16 v0 = zero, v1 = zero, v2 = zero;
+      if (valid && ih >= 0 && ih < c.H && iw >= 0 && iw < c.W) {
+        const __nv_bfloat16* p = xim + (static_cast<size_t>(ih) * c.W + iw) * 3;
+        v0 = p[0]; v1 = p[1]; v2 = p[2];
+      }
+      row[tap * 3] = v0; row[tap * 3 + 1] = v1; row[tap * 3 + 2] = v2;
+    }
+    for (int j = KT + half; j < KP; j += 2) row[j] = zero;
   }
   __syncthreads();
-  const long long npix = static_cast<long long>(c.N) * c.H * c.W;
-  const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (p >= npix) return;
-  const int ow = static_cast<int>(p % c.W);
-  const int oh = static_cast<int>((p / c.W) % c.H);
-  const int n = static_cast<int>(p / (static_cast<long long>(c.W) * c.H));
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const int r0 = warp * 16;
+  const uint32_t a_base = smem_u32(Xs + (r0 + (lane & 15)) * LDK + (lane >> 4) * 8);
+  const uint32_t b_base = smem_u32(Ws + ((lane & 7) + ((lane >> 4) << 3)) * LDK + ((lane >> 3) & 1) * 8);
+#pragma unroll 4
+  for (int ks = 0; ks < KP / 16; ++ks) {
+    uint32_t a0, a1, a2, a3;
+    ldsm_x4(a_base + ks * 32, a0, a1, a2, a3);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(b_base + (np * 16 * LDK) * 2 + ks * 32, b0, b1, b2, b3);
+      mma_bf16(acc[2 * np], a0, a1, a2, a3, b0, b1);
+      mma_bf16(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
   if (act == ACT_PRELU) slope = *slope_ptr;
   if (act == ACT_RELU) slope = 0.f;
-  const __nv_bfloat16* xn = x + static_cast<size_t>(n) * c.H * c.W * CS;
-  __nv_bfloat16* yp = y + p * c.CW;
-  for (int c0 = 0; c0 < c.CW; c0 += 16) {
-    float acc[16];
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
-    for (int kh = 0; kh < c.k; ++kh) {
-      const int ih = oh - c.pad + kh;
-      if (ih < 0 || ih >= c.H) continue;
-      for (int kw = 0; kw < c.k; ++kw) {
-        const int iw = ow - c.pad + kw;
-        if (iw < 0 || iw >= c.W) continue;
-        const __nv_bfloat16* xp = xn + (static_cast<size_t>(ih) * c.W + iw) * CS;
-        const float* wr = s_w + ((kh * c.k + kw) * CS) * c.CW + c0;
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * t;
+    const float b0 = bias ? bias[cwb + col] : 0.f, b1 = bias ? bias[cwb + col + 1] : 0.f;
+    *reinterpret_cast<uint32_t*>(Cs + (r0 + g) * kLdC + col) =
+        pack_bf16x2(act_apply(acc[nt][0] + b0, act, slope), act_apply(acc[nt][1] + b1, act, slope));
+    *reinterpret_cast<uint32_t*>(Cs + (r0 + g + 8) * kLdC + col) =
+        pack_bf16x2(act_apply(acc[nt][2] + b0, act, slope), act_apply(acc[nt][3] + b1, act, slope));
+  }
+  __syncthreads();
 #pragma unroll
-        for (int cs = 0; cs < CS; ++cs) {
-          const float xv = __bfloat162float(xp[cs]);
-          const float4* w4 = reinterpret_cast<const float4*>(wr + cs * c.CW);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 wv = w4[q];
-            acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
-          }
-        }
-      }
-    }
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      pk[j] = pack_bf16x2(act_apply(acc[2 * j], act, slope), act_apply(acc[2 * j + 1], act, slope));
-    uint4* d4 = reinterpret_cast<uint4*>(yp + c0);
-    d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * kThreads;
+    const int row = idx >> 3, chunk = idx & 7;
+    if (q0 + row < npix)
+      *reinterpret_cast<uint4*>(y + (q0 + row) * c.CW + cwb + chunk * 8) =
+          *reinterpret_cast<const uint4*>(Cs + row * kLdC + chunk * 8);
   }
 }
 
-// ------------------------------------------------------------------ thin-out: CW -> CS, k x k
-// w: [CS][k*k][CW] bf16; y_bf16: [N,H,W,CS] and/or y_nchw: [N,CS,H,W] fp32
-template <int CS>
-__global__ void __launch_bounds__(128)
-thin_out_kernel(ThinConv c, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                const float* __restrict__ bias, int act, float slope, int flip,
-                __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_nchw) {
-  extern __shared__ float s_w[];  // [tap][cw][4]
-  const int T = c.k * c.k;
-  for (int i = threadIdx.x; i < T * c.CW * 4; i += blockDim.x) {
-    const int cs = i & 3, cw = (i >> 2) % c.CW, tap = i / (4 * c.CW);
-    const int tt = flip ? T - 1 - tap : tap;
-    s_w[i] = cs < CS ? __bfloat162float(w[(static_cast<size_t>(cs) * T + tt) * c.CW + cw]) : 0.f;
+// ------------------------------------------------------------------ thin-out: 64 -> 3, 3 x 3
+// One block = R output rows of one image; the (R+2) x (W+2) x 64 input halo tile is staged once and
+// every 16-pixel group is a [16 x 576] x [576 x 8] product (3 output channels padded to 8).
+// w: [3][9][64] bf16; y_bf16: [N,H,W,3] and/or y_nchw: [N,3,H,W] fp32
+__global__ void __launch_bounds__(kThreads)
+thin_out_mma_kernel(ThinConv c, int R, const __nv_bfloat16* __restrict__ x,
+                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias, int act,
+                    float slope, int flip, __nv_bfloat16* __restrict__ y_bf16,
+                    float* __restrict__ y_nchw) {
+  constexpr int LDW = 9 * 64 + 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [8][LDW]
+  __nv_bfloat16* Xs = Ws + 8 * LDW;                                 // [(R+2)*(W+2)][kLdC]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y, row0 = blockIdx.x * R;
+  const int WP = c.W + 2;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (int i = tid; i < 8 * LDW; i += kThreads) {
+    const int cs = i / LDW, j = i - cs * LDW;
+    __nv_bfloat16 v = zero;
+    if (cs < 3 && j < 576) {
+      const int tap = j >> 6, cw = j & 63;
+      const int st = flip ? 8 - tap : tap;
+      v = w[(static_cast<size_t>(cs) * 9 + st) * 64 + cw];
+    }
+    Ws[i] = v;
   }
+  const int npos = (R + 2) * WP;
+  const __nv_bfloat16* xn = x + static_cast<size_t>(n) * c.H * c.W * 64;
+  for (int i = tid; i < npos * 8; i += kThreads) {
+    const int pix = i >> 3, ch = i & 7;
+    const int pr = pix / WP, pc = pix - pr * WP;
+    const int ih = row0 - 1 + pr, iw = pc - 1;
+    __nv_bfloat16* dst = Xs + pix * kLdC + ch * 8;
+    if (ih >= 0 && ih < c.H && iw >= 0 && iw < c.W)
+      cp_async16(smem_u32(dst), xn + (static_cast<size_t>(ih) * c.W + iw) * 64 + ch * 8);
+    else
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  }
+  cp_async_wait_all();
   __syncthreads();
-  const long long npix = static_cast<long long>(c.N) * c.H * c.W;
-  const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (p >= npix) return;
-  const int ow = static_cast<int>(p % c.W);
-  const int oh = static_cast<int>((p / c.W) % c.H);
-  const int n = static_cast<int>(p / (static_cast<long long>(c.W) * c.H));
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (bias) {
+
+  const int npx = R * c.W;
+  const int ntiles = (npx + 15) >> 4;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t b_base = smem_u32(Ws + (lane & 7) * LDW + (lane >> 3) * 8);
+  for (int mt = warp; mt < ntiles; mt += kThreads / 32) {
+    int pl = mt * 16 + (lane & 15);
+    if (pl >= npx) pl = npx - 1;
+    const int pr = pl / c.W, pc = pl - pr * c.W;
+    const uint32_t a_base = smem_u32(Xs + (pr * WP + pc) * kLdC + (lane >> 4) * 8);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int cs = 0; cs < CS; ++cs) acc[cs] = bias[cs];
-  }
-  const __nv_bfloat16* xn = x + static_cast<size_t>(n) * c.H * c.W * c.CW;
-  for (int kh = 0; kh < c.k; ++kh) {
-    const int ih = oh - c.pad + kh;
-    if (ih < 0 || ih >= c.H) continue;
-    for (int kw = 0; kw < c.k; ++kw) {
-      const int iw = ow - c.pad + kw;
-      if (iw < 0 || iw >= c.W) continue;
-      const uint4* xp = reinterpret_cast<const uint4*>(xn + (static_cast<size_t>(ih) * c.W + iw) * c.CW);
-      const float4* wt = reinterpret_cast<const float4*>(s_w) + (kh * c.k + kw) * c.CW;
-      for (int v = 0; v < c.CW / 8; ++v) {
-        const uint4 u = xp[v];
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int kh = tap / 3, kw = tap - kh * 3;
+      const uint32_t a_tap = a_base + ((kh * WP + kw) * kLdC) * 2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          const float4 w0 = wt[v * 8 + 2 * j], w1 = wt[v * 8 + 2 * j + 1];
-          acc[0] = fmaf(f.x, w0.x, acc[0]); acc[1] = fmaf(f.x, w0.y, acc[1]);
-          acc[2] = fmaf(f.x, w0.z, acc[2]);
-          acc[0] = fmaf(f.y, w1.x, acc[0]); acc[1] = fmaf(f.y, w1.y, acc[1]);
-          acc[2] = fmaf(f.y, w1.z, acc[2]);
-          if (CS == 4) { acc[3] = fmaf(f.x, w0.w, acc[3]); acc[3] = fmaf(f.y, w1.w, acc[3]); }
+      for (int kc = 0; kc < 4; kc += 2) {
+        uint32_t b0, b1, b2, b3, a0, a1, a2, a3;
+        ldsm_x4(b_base + (tap * 64 + kc * 16) * 2, b0, b1, b2, b3);
+        ldsm_x4(a_tap + kc * 32, a0, a1, a2, a3);
+        mma_bf16(acc, a0, a1, a2, a3, b0, b1);
+        ldsm_x4(a_tap + kc * 32 + 32, a0, a1, a2, a3);
+        mma_bf16(acc, a0, a1, a2, a3, b2, b3);
+      }
+    }
+    if (t < 2) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int p = mt * 16 + g + hh * 8;
+        const int oh = row0 + p / c.W, ow = p % c.W;
+        if (p >= npx || oh >= c.H) continue;
+        const size_t q = (static_cast<size_t>(n) * c.H + oh) * c.W + ow;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cs = 2 * t + e;
+          if (cs >= 3) continue;
+          const float v = act_apply(acc[hh * 2 + e] + (bias ? bias[cs] : 0.f), act, slope);
+          if (y_bf16) y_bf16[q * 3 + cs] = __float2bfloat16_rn(v);
+          if (y_nchw) y_nchw[((static_cast<size_t>(n) * 3 + cs) * c.H + oh) * c.W + ow] = v;
         }
       }
     }
-  }
-#pragma unroll
-  for (int cs = 0; cs < CS; ++cs) {
-    const float v = act_apply(acc[cs], act, slope);
-    if (y_bf16) y_bf16[p * CS + cs] = __float2bfloat16_rn(v);
-    if (y_nchw) y_nchw[((static_cast<size_t>(n) * CS + cs) * c.H + oh) * c.W + ow] = v;
   }
 }
 
 // ------------------------------------------------------------------ thin wgrad
-// G[cs, tap, cw] = sum_q Wt[q, cw] * S[q + sgn*(tap - pad), cs]
-//   type A (sgn=+1): S = input x (CS ch), Wt = dy (CW ch): out[(cw*T + tap)*CS + cs]
-//   type B (sgn=-1): S = dy (CS ch), Wt = input x (CW ch): out[(cs*T + tap)*CW + cw]
-// Block = 16 channel-quads x G combo groups x PZ pixels in flight; fp32 atomics into `out`.
-template <int CS, int KK, int G>
-__global__ void __launch_bounds__(256)
-thin_wgrad_kernel(ThinConv c, const __nv_bfloat16* __restrict__ s, const __nv_bfloat16* __restrict__ wt,
-                  int sgn, float* __restrict__ out) {
-  constexpr int PZ = 256 / (16 * G);
-  const int T = c.k * c.k;
-  const int combos = T * CS;
-  const int cq = threadIdx.x % 16;
-  const int g = (threadIdx.x / 16) % G;
-  const int pz = threadIdx.x / (16 * G);
-  const int cw0 = blockIdx.y * 64 + cq * 4;
-  int dh[KK], dw[KK], cs_[KK];
-  bool on[KK];
-#pragma unroll
-  for (int i = 0; i < KK; ++i) {
-    const int j = g + G * i;
-    on[i] = j < combos;
-    const int tap = on[i] ? j / CS : 0;
-    cs_[i] = on[i] ? j % CS : 0;
-    dh[i] = sgn * (tap / c.k - c.pad);
-    dw[i] = sgn * (tap % c.k - c.pad);
-  }
-  float acc[KK][4];
-#pragma unroll
-  for (int i = 0; i < KK; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+// G[cw, j] = sum_q wide[q, cw] * small[q + sgn*(tap - pad), cs],  j = tap*3 + cs
+//   type A (sgn=+1): small = input x, wide = dy:  out[(cw*T + tap)*3 + cs]
+//   type B (sgn=-1): small = dy, wide = input x:  out[(cs*T + tap)*CW + cw]
+// GEMM with K = pixels: A = wide^T (ldmatrix.trans from the staged [pixels][64] tile), B = the
+// transposed im2col XT[j][pixel] built in shared memory; column j = T*3 of XT is all ones, which
+// yields sum_q wide[q, cw] (the bias gradient of a thin-in conv) for free.
+// NS = number of 32-column slices of j: 1 (3x3: the 8 warps split the pixels of a tile) or
+// 8 (9x9: the 8 warps split j).  fp32 atomics into `out` (zeroed by the caller).
+template <int NS>
+__global__ void __launch_bounds__(kThreads)
+thin_wgrad_mma_kernel(ThinConv c, const __nv_bfloat16* __restrict__ small,
+                      const __nv_bfloat16* __restrict__ wide, int sgn, float* __restrict__ out,
+                      float* __restrict__ wide_colsum, int ntiles) {
+  constexpr int NP = NS * 32;
+  constexpr int LDQ = kTileQ + 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* Wd = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [128][kLdC]
+  __nv_bfloat16* XT = Wd + kTileQ * kLdC;                           // [NP][LDQ]
+  const int T = c.k * c.k, KT = T * 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cwb = blockIdx.y * 64;
   const long long npix = static_cast<long long>(c.N) * c.H * c.W;
-  const long long per = (npix + gridDim.x - 1) / gridDim.x;
-  const long long q0 = blockIdx.x * per;
-  const long long q1 = q0 + per < npix ? q0 + per : npix;
-  for (long long q = q0 + pz; q < q1; q += PZ) {
-    const int qw = static_cast<int>(q % c.W);
-    const int qh = static_cast<int>((q / c.W) % c.H);
-    const long long nbase = q - (static_cast<long long>(qh) * c.W + qw);   // first pixel of the image
-    const uint2 u = *reinterpret_cast<const uint2*>(wt + q * c.CW + cw0);
-    const float2 f01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-    const float2 f23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
+
+  float acc[4][4][4];
 #pragma unroll
-    for (int i = 0; i < KK; ++i) {
-      const int ih = qh + dh[i], iw = qw + dw[i];
-      if (on[i] && ih >= 0 && ih < c.H && iw >= 0 && iw < c.W) {
-        const float sv = __bfloat162float(s[(nbase + static_cast<long long>(ih) * c.W + iw) * CS + cs_[i]]);
-        acc[i][0] = fmaf(sv, f01.x, acc[i][0]);
-        acc[i][1] = fmaf(sv, f01.y, acc[i][1]);
-        acc[i][2] = fmaf(sv, f23.x, acc[i][2]);
-        acc[i][3] = fmaf(sv, f23.y, acc[i][3]);
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+
+  for (int j = KT + 1 + (tid >> 7); j < NP; j += 2) XT[j * LDQ + (tid & 127)] = zero;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long q0 = static_cast<long long>(tile) * kTileQ;
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * kThreads;
+      const int row = idx >> 3, chunk = idx & 7;
+      __nv_bfloat16* dst = Wd + row * kLdC + chunk * 8;
+      if (q0 + row < npix)
+        cp_async16(smem_u32(dst), wide + (q0 + row) * c.CW + cwb + chunk * 8);
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    {
+      const int ql = tid & 127, half = tid >> 7;
+      const long long q = q0 + ql;
+      const bool valid = q < npix;
+      const long long qq = valid ? q : 0;
+      const int qw = static_cast<int>(qq % c.W);
+      const int qh = static_cast<int>((qq / c.W) % c.H);
+      for (int tap = half; tap < T; tap += 2) {
+        const int dh = sgn * (tap / c.k - c.pad), dw = sgn * (tap % c.k - c.pad);
+        const int ih = qh + dh, iw = qw + dw;
+        __nv_bfloat16 v0 = zero, v1 = zero, v2 = zero;
+        if (valid && ih >= 0 && ih < c.H && iw >= 0 && iw < c.W) {
+          const __nv_bfloat16* p = small + (qq + dh * c.W + dw) * 3;
+          v0 = p[0]; v1 = p[1]; v2 = p[2];
+        }
+        XT[(tap * 3) * LDQ + ql] = v0;
+        XT[(tap * 3 + 1) * LDQ + ql] = v1;
+        XT[(tap * 3 + 2) * LDQ + ql] = v2;
+      }
+      if (half == 0) XT[KT * LDQ + ql] = valid ? one : zero;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const int ns = NS == 1 ? 0 : warp;
+    const int ks_begin = NS == 1 ? warp : 0;
+    const int ks_end = NS == 1 ? warp + 1 : kTileQ / 16;
+    for (int ks = ks_begin; ks < ks_end; ++ks) {
+      uint32_t a[4][4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+        ldsm_x4_trans(smem_u32(Wd + (ks * 16 + (lane & 7) + ((lane >> 4) << 3)) * kLdC + mt * 16 +
+                               ((lane >> 3) & 1) * 8),
+                      a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(smem_u32(XT + (ns * 32 + np * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDQ + ks * 16 +
+                         ((lane >> 3) & 1) * 8),
+                b0, b1, b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          mma_bf16(acc[mt][2 * np], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+          mma_bf16(acc[mt][2 * np + 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b2, b3);
+        }
       }
     }
   }
-  // combine the PZ pixel groups in shared memory, then one global atomic per (combo, channel)
-  constexpr int kRed = (PZ > 1) ? KK * G * 64 : 1;
-  __shared__ float s_red[kRed];
-  if (PZ > 1) {
-    for (int i = threadIdx.x; i < kRed; i += blockDim.x) s_red[i] = 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < KK; ++i) {
-      if (!on[i]) continue;
-      const int j = g + G * i;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) atomicAdd(&s_red[j * 64 + cq * 4 + e], acc[i][e]);
+
+  const int g = lane >> 2, t = lane & 3;
+  auto emit = [&](int cw, int j, float v) {
+    if (j < KT) {
+      const int tap = j / 3, cs = j - tap * 3;
+      float* dst = (sgn > 0) ? out + static_cast<size_t>(cwb + cw) * KT + j
+                             : out + (static_cast<size_t>(cs) * T + tap) * c.CW + cwb + cw;
+      atomicAdd(dst, v);
+    } else if (j == KT && wide_colsum) {
+      atomicAdd(&wide_colsum[cwb + cw], v);
     }
+  };
+  if (NS == 1) {
+    // combine the 8 warps' partial sums (disjoint pixel ranges) in shared memory
     __syncthreads();
-    for (int i = threadIdx.x; i < combos * 64; i += blockDim.x) {
-      const int j = i / 64, cl = i % 64;
-      const int tap = j / CS, cs = j % CS, cw = blockIdx.y * 64 + cl;
-      float* dst = (sgn > 0) ? out + (static_cast<size_t>(cw) * T + tap) * CS + cs
-                             : out + (static_cast<size_t>(cs) * T + tap) * c.CW + cw;
-      atomicAdd(dst, s_red[i]);
+    float* red = reinterpret_cast<float*>(smem_raw);   // [64][33] over the Wd region
+    for (int wv = 0; wv < kThreads / 32; ++wv) {
+      if (warp == wv) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int m = mt * 16 + g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
+              float* r = red + m * 33 + j;
+              *r = (wv == 0) ? acc[mt][nt][e] : *r + acc[mt][nt][e];
+            }
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < 64 * (KT + 1); i += kThreads) {
+      const int cw = i / (KT + 1), j = i - cw * (KT + 1);
+      emit(cw, j, red[cw * 33 + j]);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < KK; ++i) {
-      if (!on[i]) continue;
-      const int j = g + G * i;
-      const int tap = j / CS;
+    for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int cw = cw0 + e;
-        float* dst = (sgn > 0) ? out + (static_cast<size_t>(cw) * T + tap) * CS + cs_[i]
-                               : out + (static_cast<size_t>(cs_[i]) * T + tap) * c.CW + cw;
-        atomicAdd(dst, acc[i][e]);
-      }
-    }
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          emit(mt * 16 + g + (e >> 1) * 8, warp * 32 + nt * 8 + 2 * t + (e & 1), acc[mt][nt][e]);
   }
 }
 
@@ -262,56 +405,85 @@ int check(const char* what) {
   return 4;
 }
 
+template <typename K>
+int set_smem(K kernel, int bytes, int* configured) {
+  if (bytes > *configured) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
+      return check("cudaFuncSetAttribute");
+    *configured = bytes;
+  }
+  return 0;
+}
+
+constexpr int kSmemLimit = 220 * 1024;
+
+int thin_out_rows(const ThinConv& c) {
+  for (int r = 4; r >= 1; r >>= 1) {
+    const int rr = r < c.H ? r : c.H;
+    if ((8 * (9 * 64 + 8) + (rr + 2) * (c.W + 2) * kLdC) * 2 <= 100 * 1024 || r == 1) return rr;
+  }
+  return 1;
+}
+
 }  // namespace
 
 const char* thin_last_error() { return g_err; }
 
-bool thin_in_supported(const ThinConv& c) { return c.CS == 3 && c.CW % 16 == 0 && c.CW * c.k * c.k * c.CS * 4 <= 200 * 1024; }
-bool thin_out_supported(const ThinConv& c) { return c.CS == 3 && c.CW % 8 == 0 && c.k * c.k * c.CW * 16 <= 200 * 1024; }
+bool thin_in_supported(const ThinConv& c) { return c.CS == 3 && c.CW % 64 == 0 && (c.k == 3 || c.k == 9); }
+bool thin_out_supported(const ThinConv& c) {
+  return c.CS == 3 && c.CW == 64 && c.k == 3 &&
+         (8 * (9 * 64 + 8) + 3 * (c.W + 2) * kLdC) * 2 <= kSmemLimit;
+}
 bool thin_wgrad_supported(const ThinConv& c) { return c.CS == 3 && c.CW % 64 == 0 && (c.k == 3 || c.k == 9); }
 
 int thin_in_conv(const ThinConv& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias,
                  int act, float slope, const float* slope_ptr, int flip, __nv_bfloat16* y,
                  cudaStream_t s) {
-  const int smem = c.CW * c.k * c.k * c.CS * sizeof(float);
-  static int configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(thin_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = smem;
-  }
   const long long npix = static_cast<long long>(c.N) * c.H * c.W;
-  thin_in_kernel<3><<<static_cast<int>((npix + 127) / 128), 128, smem, s>>>(c, x, w, bias, act, slope,
-                                                                           slope_ptr, flip, y);
+  dim3 grid(static_cast<unsigned>((npix + kTileQ - 1) / kTileQ), c.CW / 64);
+  if (c.k == 3) {
+    constexpr int KP = 32;
+    const int smem = ((64 + kTileQ) * (KP + 8) + kTileQ * kLdC) * 2;
+    thin_in_mma_kernel<KP><<<grid, kThreads, smem, s>>>(c, x, w, bias, act, slope, slope_ptr, flip, y);
+  } else {
+    constexpr int KP = 256;
+    const int smem = ((64 + kTileQ) * (KP + 8) + kTileQ * kLdC) * 2;
+    static int configured = 0;
+    if (int rc = set_smem(thin_in_mma_kernel<KP>, smem, &configured)) return rc;
+    thin_in_mma_kernel<KP><<<grid, kThreads, smem, s>>>(c, x, w, bias, act, slope, slope_ptr, flip, y);
+  }
   return check("thin_in_conv");
 }
 
 int thin_out_conv(const ThinConv& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias,
                   int act, float slope, int flip, __nv_bfloat16* y_bf16, float* y_nchw, cudaStream_t s) {
-  const int smem = c.k * c.k * c.CW * 4 * sizeof(float);
+  const int R = thin_out_rows(c);
+  const int smem = (8 * (9 * 64 + 8) + (R + 2) * (c.W + 2) * kLdC) * 2;
   static int configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(thin_out_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = smem;
-  }
-  const long long npix = static_cast<long long>(c.N) * c.H * c.W;
-  thin_out_kernel<3><<<static_cast<int>((npix + 127) / 128), 128, smem, s>>>(c, x, w, bias, act, slope,
-                                                                            flip, y_bf16, y_nchw);
+  if (int rc = set_smem(thin_out_mma_kernel, smem, &configured)) return rc;
+  dim3 grid((c.H + R - 1) / R, c.N);
+  thin_out_mma_kernel<<<grid, kThreads, smem, s>>>(c, R, x, w, bias, act, slope, flip, y_bf16, y_nchw);
   return check("thin_out_conv");
 }
 
 int thin_wgrad(const ThinConv& c, const __nv_bfloat16* small, const __nv_bfloat16* wide, int sgn,
-               float* out, float* small_colsum, cudaStream_t s) {
+               float* out, float* small_colsum, float* wide_colsum, cudaStream_t s) {
   const int T = c.k * c.k;
   cudaMemsetAsync(out, 0, sizeof(float) * T * c.CS * c.CW, s);
+  if (wide_colsum) cudaMemsetAsync(wide_colsum, 0, sizeof(float) * c.CW, s);
   const long long npix = static_cast<long long>(c.N) * c.H * c.W;
-  long long gx = (npix + 511) / 512;
-  if (gx > 148 * 2) gx = 148 * 2;
-  if (gx < 1) gx = 1;
-  dim3 grid(static_cast<unsigned>(gx), c.CW / 64);
-  if (c.k == 3)
-    thin_wgrad_kernel<3, 7, 4><<<grid, 256, 0, s>>>(c, small, wide, sgn, out);
-  else
-    thin_wgrad_kernel<3, 16, 16><<<grid, 256, 0, s>>>(c, small, wide, sgn, out);
+  const int ntiles = static_cast<int>((npix + kTileQ - 1) / kTileQ);
+  if (c.k == 3) {
+    const int smem = (kTileQ * kLdC + 32 * (kTileQ + 8)) * 2;
+    dim3 grid(ntiles < 148 * 4 ? ntiles : 148 * 4, c.CW / 64);
+    thin_wgrad_mma_kernel<1><<<grid, kThreads, smem, s>>>(c, small, wide, sgn, out, wide_colsum, ntiles);
+  } else {
+    const int smem = (kTileQ * kLdC + 256 * (kTileQ + 8)) * 2;
+    static int configured = 0;
+    if (int rc = set_smem(thin_wgrad_mma_kernel<8>, smem, &configured)) return rc;
+    dim3 grid(ntiles < 148 ? ntiles : 148, c.CW / 64);
+    thin_wgrad_mma_kernel<8><<<grid, kThreads, smem, s>>>(c, small, wide, sgn, out, wide_colsum, ntiles);
+  }
   if (small_colsum) {
     cudaMemsetAsync(small_colsum, 0, sizeof(float) * c.CS, s);
     thin_colsum_kernel<3><<<148, 256, 0, s>>>(small, npix, small_colsum);

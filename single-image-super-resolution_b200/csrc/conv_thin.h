@@ -24,9 +24,10 @@ int thin_out_conv(const ThinConv& c, const __nv_bfloat16* x, const __nv_bfloat16
                   int act, float slope, int flip, __nv_bfloat16* y_bf16, float* y_nchw, cudaStream_t s);
 // sgn=+1: out[cw][tap][cs] = sum_q wide[q,cw]*small[q+(tap-pad),cs]   (weight grad of a thin-in conv)
 // sgn=-1: out[cs][tap][cw] = sum_q wide[q,cw]*small[q-(tap-pad),cs]   (weight grad of a thin-out conv)
-// small_colsum (nullable): [CS] per-channel sum of `small`
+// small_colsum (nullable): [CS] per-channel sum of `small`; wide_colsum (nullable): [CW] per-channel
+// sum of `wide` (both overwritten)
 int thin_wgrad(const ThinConv& c, const __nv_bfloat16* small, const __nv_bfloat16* wide, int sgn,
-               float* out, float* small_colsum, cudaStream_t s);
+               float* out, float* small_colsum, float* wide_colsum, cudaStream_t s);
 const char* thin_last_error();
 
 }  // namespace sisr

@@ -237,23 +237,51 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
   }
 }
 
+// ------------------------------------------------------------------ per-channel block reductions
+// Thread (r, cv) of a 256-thread block owns channels [8cv, 8cv+8) of the rows r, r+rpb, ... it
+// visits (tpr = C/8 threads per row, rpb = 256/tpr rows in flight).  After the row loop the NQ
+// per-thread partial vectors are combined without atomics: staged as s_red[q][r][C], summed over r
+// by one thread per column, and added to global memory once per column per block.
+constexpr int kRedFloats = 2048;   // rpb * C for every supported C (C % 8 == 0, C <= 2048)
+template <int NQ>
+__device__ __forceinline__ void block_col_reduce(const float (&p)[NQ][8], int r, int cv, int rpb, int C,
+                                                 bool active, float* s_red, float* const (&out)[NQ]) {
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float4* d = reinterpret_cast<float4*>(s_red + (q * rpb + r) * C + cv * 8);
+      d[0] = make_float4(p[q][0], p[q][1], p[q][2], p[q][3]);
+      d[1] = make_float4(p[q][4], p[q][5], p[q][6], p[q][7]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * C; i += blockDim.x) {
+    const int q = i / C, c = i - q * C;
+    if (!out[q]) continue;
+    float acc = 0.f;
+    for (int rr = 0; rr < rpb; ++rr) acc += s_red[(q * rpb + rr) * C + c];
+    atomicAdd(out[q] + c, acc);
+  }
+}
+
 // ------------------------------------------------------------------ BatchNorm backward
 // sums[0..C) += sum g, sums[C..2C) += sum g*xhat, sums[2C] += sum dout*min(0,z)   (g = dout*act'(z))
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout,
-                                     const __nv_bfloat16* __restrict__ y,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                     int act, float slope, const float* __restrict__ slope_ptr,
-                                     float* __restrict__ sums, long long M, int C) {
-  extern __shared__ float s_acc[];  // [2*C + 1]
-  for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ y,
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                     float slope, const float* __restrict__ slope_ptr, float* __restrict__ sums,
+                     long long M, int C) {
+  __shared__ __align__(16) float s_red[2 * kRedFloats];
+  __shared__ float s_sa[kThreads / 32];
   const float sl = resolve_slope(act, slope, slope_ptr);
   const int tpr = C / 8;
   const int rpb = blockDim.x / tpr;
   const int r = threadIdx.x / tpr, cv = threadIdx.x % tpr;
-  float s1[8] = {0}, s2[8] = {0}, sa = 0.f;
-  if (r < rpb) {
+  const bool active = r < rpb;
+  float p[2][8] = {};
+  float sa = 0.f;
+  if (active) {
     float mu[8], is[8], sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -270,78 +298,113 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout,
       for (int j = 0; j < 8; ++j) {
         const float z = fmaf(v.v[j], sc[j], sh[j]);
         const float g = d.v[j] * act_grad(z, act, sl);
-        s1[j] += g;
-        s2[j] += g * (v.v[j] - mu[j]) * is[j];
+        p[0][j] += g;
+        p[1][j] += g * (v.v[j] - mu[j]) * is[j];
         if (act == ACT_PRELU) sa += d.v[j] * fminf(z, 0.f);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_acc[cv * 8 + j], s1[j]);
-      atomicAdd(&s_acc[C + cv * 8 + j], s2[j]);
-    }
   }
+  float* const outs[2] = {sums, sums + C};
+  block_col_reduce<2>(p, r, cv, rpb, C, active, s_red, outs);
   if (act == ACT_PRELU) {
     sa = warp_sum(sa);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[2 * C], sa);
+    if ((threadIdx.x & 31) == 0) s_sa[threadIdx.x >> 5] = sa;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < kThreads / 32; ++i) t += s_sa[i];
+      atomicAdd(&sums[2 * C], t);
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C + (act == ACT_PRELU ? 1 : 0); i += blockDim.x)
-    atomicAdd(&sums[i], s_acc[i]);
 }
 
-// dy = gamma*invstd * (g - sum_g/count - xhat * sum_gx/count)
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout,
-                                    const __nv_bfloat16* __restrict__ y,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    int act, float slope, const float* __restrict__ slope_ptr,
-                                    const float* __restrict__ sums, float inv_count,
-                                    __nv_bfloat16* __restrict__ dy, long long nvec, int C) {
+// dy = gamma*invstd * (g - sum_g/count - xhat * sum_gx/count);  colsum[c] += sum_rows dy (as stored)
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ y,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                    float slope, const float* __restrict__ slope_ptr, const float* __restrict__ sums,
+                    float inv_count, __nv_bfloat16* __restrict__ dy, float* __restrict__ colsum,
+                    long long M, int C) {
+  __shared__ __align__(16) float s_red[kRedFloats];
   const float sl = resolve_slope(act, slope, slope_ptr);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>((i * 8) % C);
-    const Vec8 d = load8(dout + i * 8);
-    const Vec8 v = load8(y + i * 8);
-    Vec8 o;
+  const int tpr = C / 8;
+  const int rpb = blockDim.x / tpr;
+  const int r = threadIdx.x / tpr, cv = threadIdx.x % tpr;
+  const bool active = r < rpb;
+  float p[1][8] = {};
+  if (active) {
+    float mu[8], is[8], sc[8], sh[8], k1[8], k2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float sc = scale[c];
-      const float z = fmaf(v.v[j], sc, shift[c]);
-      const float g = d.v[j] * act_grad(z, act, sl);
-      const float xh = (v.v[j] - mean[c]) * invstd[c];
-      o.v[j] = sc * (g - sums[c] * inv_count - xh * sums[C + c] * inv_count);
+      const int c = cv * 8 + j;
+      mu[j] = mean[c];
+      is[j] = invstd[c];
+      sc[j] = scale[c];
+      sh[j] = shift[c];
+      k1[j] = sums[c] * inv_count;
+      k2[j] = sums[C + c] * inv_count;
     }
-    store8(dy + i * 8, o);
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < M;
+         row += static_cast<long long>(gridDim.x) * rpb) {
+      const Vec8 d = load8(dout + row * C + cv * 8);
+      const Vec8 v = load8(y + row * C + cv * 8);
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(v.v[j], sc[j], sh[j]);
+        const float g = d.v[j] * act_grad(z, act, sl);
+        const float xh = (v.v[j] - mu[j]) * is[j];
+        o.v[j] = bf16_round(sc[j] * (g - k1[j] - xh * k2[j]));
+        p[0][j] += o.v[j];
+      }
+      store8(dy + row * C + cv * 8, o);
+    }
+  }
+  if (colsum) {
+    float* const outs[1] = {colsum};
+    block_col_reduce<1>(p, r, cv, rpb, C, active, s_red, outs);
   }
 }
 
 // ------------------------------------------------------------------ activation backward (from output)
-// din = dout * (out > 0 ? 1 : slope); dslope += sum_{out<0} dout*out/slope   (requires slope > 0)
-__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
-                               const __nv_bfloat16* __restrict__ out, int act, float slope,
-                               const float* __restrict__ slope_ptr, __nv_bfloat16* __restrict__ din,
-                               float* __restrict__ dslope, long long nvec) {
+// din = dout * (out > 0 ? 1 : slope); dslope += sum_{out<0} dout*out/slope   (requires slope > 0);
+// colsum[c] += sum_rows din (as stored)
+__global__ void __launch_bounds__(kThreads)
+act_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, int act,
+               float slope, const float* __restrict__ slope_ptr, __nv_bfloat16* __restrict__ din,
+               float* __restrict__ dslope, float* __restrict__ colsum, long long M, int C) {
+  __shared__ __align__(16) float s_red[kRedFloats];
+  __shared__ float s_part[kThreads / 32];
   const float sl = resolve_slope(act, slope, slope_ptr);
   const float inv_sl = sl != 0.f ? 1.f / sl : 0.f;
+  const int tpr = C / 8;
+  const int rpb = blockDim.x / tpr;
+  const int r = threadIdx.x / tpr, cv = threadIdx.x % tpr;
+  const bool active = r < rpb;
+  float p[1][8] = {};
   float sa = 0.f;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const Vec8 d = load8(dout + i * 8);
-    const Vec8 o = load8(out + i * 8);
-    Vec8 r;
+  if (active) {
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < M;
+         row += static_cast<long long>(gridDim.x) * rpb) {
+      const Vec8 d = load8(dout + row * C + cv * 8);
+      const Vec8 o = load8(out + row * C + cv * 8);
+      Vec8 q;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const bool pos = o.v[j] > 0.f;
-      r.v[j] = pos ? d.v[j] : d.v[j] * sl;
-      if (!pos) sa += d.v[j] * o.v[j] * inv_sl;
+      for (int j = 0; j < 8; ++j) {
+        const bool pos = o.v[j] > 0.f;
+        q.v[j] = bf16_round(pos ? d.v[j] : d.v[j] * sl);
+        p[0][j] += q.v[j];
+        if (!pos) sa += d.v[j] * o.v[j] * inv_sl;
+      }
+      store8(din + row * C + cv * 8, q);
     }
-    store8(din + i * 8, r);
+  }
+  if (colsum) {
+    float* const outs[1] = {colsum};
+    block_col_reduce<1>(p, r, cv, rpb, C, active, s_red, outs);
   }
   if (dslope) {
-    __shared__ float s_part[kThreads / 32];
     sa = warp_sum(sa);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sa;
     __syncthreads();
@@ -546,25 +609,27 @@ int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float
                   const float* slope_ptr, float* sums, long long M, int C, cudaStream_t s) {
   if (C % 8 || C / 8 > kThreads) return 1;
   const int rpb = kThreads / (C / 8);
-  bn_bwd_reduce_kernel<<<grid_for(M, rpb, 148 * 4), kThreads, (2 * C + 1) * sizeof(float), s>>>(
+  bn_bwd_reduce_kernel<<<grid_for(M, rpb * 4, 148 * 2), kThreads, 0, s>>>(
       dout, y, mean, invstd, scale, shift, act, slope, slope_ptr, sums, M, C);
   return check();
 }
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float* mean,
                  const float* invstd, const float* scale, const float* shift, int act, float slope,
                  const float* slope_ptr, const float* sums, float count, __nv_bfloat16* dy,
-                 long long M, int C, cudaStream_t s) {
-  if (C % 8) return 1;
-  const long long nvec = M * C / 8;
-  bn_bwd_apply_kernel<<<grid_for(nvec, kThreads), kThreads, 0, s>>>(
-      dout, y, mean, invstd, scale, shift, act, slope, slope_ptr, sums, 1.f / count, dy, nvec, C);
+                 float* colsum, long long M, int C, cudaStream_t s) {
+  if (C % 8 || C / 8 > kThreads) return 1;
+  const int rpb = kThreads / (C / 8);
+  bn_bwd_apply_kernel<<<grid_for(M, rpb * 4, 148 * 4), kThreads, 0, s>>>(
+      dout, y, mean, invstd, scale, shift, act, slope, slope_ptr, sums, 1.f / count, dy, colsum, M, C);
   return check();
 }
 int act_bwd(const __nv_bfloat16* dout, const __nv_bfloat16* out, int act, float slope,
-            const float* slope_ptr, __nv_bfloat16* din, float* dslope, long long n, cudaStream_t s) {
-  if (n % 8) return 1;
-  act_bwd_kernel<<<grid_for(n / 8, kThreads, 148 * 8), kThreads, 0, s>>>(dout, out, act, slope,
-                                                                         slope_ptr, din, dslope, n / 8);
+            const float* slope_ptr, __nv_bfloat16* din, float* dslope, float* colsum, long long M, int C,
+            cudaStream_t s) {
+  if (C % 8 || C / 8 > kThreads) return 1;
+  const int rpb = kThreads / (C / 8);
+  act_bwd_kernel<<<grid_for(M, rpb * 4, 148 * 4), kThreads, 0, s>>>(dout, out, act, slope, slope_ptr, din,
+                                                                    dslope, colsum, M, C);
   return check();
 }
 int maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int N, int H, int W, int C,

@@ -28,9 +28,10 @@ int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float* mean,
                  const float* invstd, const float* scale, const float* shift, int act, float slope,
                  const float* slope_ptr, const float* sums, float count, __nv_bfloat16* dy,
-                 long long M, int C, cudaStream_t s);
+                 float* colsum, long long M, int C, cudaStream_t s);
 int act_bwd(const __nv_bfloat16* dout, const __nv_bfloat16* out, int act, float slope,
-            const float* slope_ptr, __nv_bfloat16* din, float* dslope, long long n, cudaStream_t s);
+            const float* slope_ptr, __nv_bfloat16* din, float* dslope, float* colsum, long long M, int C,
+            cudaStream_t s);
 int maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int N, int H, int W, int C, cudaStream_t s);
 int maxpool2_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16* dx, int N, int H,
                  int W, int C, cudaStream_t s);

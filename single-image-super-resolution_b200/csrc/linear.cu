@@ -1,78 +1,182 @@
 // Discriminator head: Linear(fc_in -> fc_mid) + LeakyReLU + Linear(fc_mid -> 1) + Sigmoid,
-// forward and backward.  The large GEMMs run on a strided CUDA-core tile kernel that reads the
-// fp32 master weight in its native [fc_mid, C*H*W] layout (the activations are permuted to the
-// reference's (c,h,w) flatten order instead of permuting the 19 M-element weight).
+// forward and backward.  The three skinny GEMMs (batch x 18432 x 1024) are HBM-bound on the 75 MB
+// fp32 master weight, which is read in its native [fc_mid, C*H*W] layout (the activations are
+// permuted to the reference's (c,h,w) flatten order instead of permuting the 19 M-element weight)
+// and rounded to bf16 on the way into shared memory; the contraction is warp-level mma.sync.
 #include "linear.h"
 
 #include <stdio.h>
+
+#include "ptx.cuh"
 
 namespace sisr {
 
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int kTile = 64;      // block tile is 64 x 64 x 64
+constexpr int kLd = kTile + 8; // bf16 row stride of a staged tile (144 B: conflict-free ldmatrix)
 
-__device__ __forceinline__ float to_f(float v) { return v; }
-__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
-
-// C[m,n] (+)= sum_k A(m,k) * B(n,k);  A(m,k) = a[m*sam + k*sak], B(n,k) = b[n*sbn + k*sbk]
-template <typename TA, typename TB>
-__global__ void __launch_bounds__(256)
-gemm_simt_kernel(const TA* __restrict__ a, long long sam, long long sak, const TB* __restrict__ b,
-                 long long sbn, long long sbk, float* __restrict__ c, long long ldc, int M, int N,
-                 int K, int k_per_split) {
-  __shared__ float As[TK][TM + 4];
-  __shared__ float Bs[TK][TN + 4];
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-  const int kbeg = blockIdx.z * k_per_split;
-  const int kend = min(K, kbeg + k_per_split);
-  const int t = threadIdx.x;
-  const int tx = t % 16, ty = t / 16;
-  float acc[4][4] = {};
-  for (int k0 = kbeg; k0 < kend; k0 += TK) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int m, k;
-      if (sak == 1) { k = t % TK; m = t / TK + 16 * j; } else { m = t % TM; k = t / TM + 4 * j; }
-      const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < kend) ? to_f(a[gm * sam + gk * sak]) : 0.f;
-      int n, kk;
-      if (sbk == 1) { kk = t % TK; n = t / TK + 16 * j; } else { n = t % TN; kk = t / TN + 4 * j; }
-      const int gn = n0 + n, gk2 = k0 + kk;
-      Bs[kk][n] = (gn < N && gk2 < kend) ? to_f(b[gn * sbn + gk2 * sbk]) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < TK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float ar[4] = {av.x, av.y, av.z, av.w};
-      const float br[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
-    if (gm >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
-      if (gn >= N) continue;
-      float* dst = c + gm * ldc + gn;
-      if (gridDim.z > 1) atomicAdd(dst, acc[i][j]); else *dst = acc[i][j];
-    }
-  }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                              uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <typename TA, typename TB>
-int launch_gemm(const TA* a, long long sam, long long sak, const TB* b, long long sbn, long long sbk,
-                float* c, long long ldc, int M, int N, int K, cudaStream_t s) {
-  const int tiles = ((M + TM - 1) / TM) * ((N + TN - 1) / TN);
+// 16 consecutive elements of one source row -> 16 bf16 (8 packed words); zero outside [0, valid)
+struct Row16 {
+  uint32_t w[8];
+};
+__device__ __forceinline__ Row16 load_row16(const float* p, int valid) {
+  Row16 r;
+  if (valid >= 16 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(p4 + i);
+      r.w[2 * i] = pack_bf16x2(v.x, v.y);
+      r.w[2 * i + 1] = pack_bf16x2(v.z, v.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      r.w[i] = pack_bf16x2(2 * i < valid ? p[2 * i] : 0.f, 2 * i + 1 < valid ? p[2 * i + 1] : 0.f);
+  }
+  return r;
+}
+__device__ __forceinline__ Row16 load_row16(const __nv_bfloat16* p, int valid) {
+  Row16 r;
+  if (valid >= 16 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    r.w[0] = u0.x; r.w[1] = u0.y; r.w[2] = u0.z; r.w[3] = u0.w;
+    r.w[4] = u1.x; r.w[5] = u1.y; r.w[6] = u1.z; r.w[7] = u1.w;
+  } else {
+    const unsigned short* q = reinterpret_cast<const unsigned short*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t lo = 2 * i < valid ? q[2 * i] : 0u, hi = 2 * i + 1 < valid ? q[2 * i + 1] : 0u;
+      r.w[i] = lo | (hi << 16);
+    }
+  }
+  return r;
+}
+
+// C[M,N] (+)= sum_k A(m,k) * B(n,k) on warp-level mma.sync tiles (bf16 inputs, fp32 accumulate);
+// fp32 operands are rounded to bf16 while they are staged into shared memory.
+//   AK: A(m,k) = a[m*lda + k]  (k contiguous)   else A(m,k) = a[k*lda + m]
+//   BK: B(n,k) = b[n*ldb + k]                   else B(n,k) = b[k*ldb + n]
+// The staged tiles keep the source's contiguous dimension, ldmatrix(.trans) builds the fragments.
+// gridDim.z > 1: split-K with fp32 atomics into a zeroed C.
+template <typename TA, typename TB, bool AK, bool BK>
+__global__ void __launch_bounds__(256)
+gemm_mma_kernel(const TA* __restrict__ a, long long lda, const TB* __restrict__ b, long long ldb,
+                float* __restrict__ c, long long ldc, int M, int N, int K, int k_per_split) {
+  __shared__ __align__(16) __nv_bfloat16 As[2][kTile * kLd];
+  __shared__ __align__(16) __nv_bfloat16 Bs[2][kTile * kLd];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int lrow = tid >> 2, lseg = (tid & 3) * 16;
+  auto fetch_a = [&](int k0) {
+    if (AK) {
+      const int m = m0 + lrow, k = k0 + lseg;
+      return load_row16(a + static_cast<long long>(m) * lda + k, m < M ? kend - k : 0);
+    }
+    const int k = k0 + lrow, m = m0 + lseg;
+    return load_row16(a + static_cast<long long>(k) * lda + m, k < kend ? M - m : 0);
+  };
+  auto fetch_b = [&](int k0) {
+    if (BK) {
+      const int n = n0 + lrow, k = k0 + lseg;
+      return load_row16(b + static_cast<long long>(n) * ldb + k, n < N ? kend - k : 0);
+    }
+    const int k = k0 + lrow, n = n0 + lseg;
+    return load_row16(b + static_cast<long long>(k) * ldb + n, k < kend ? N - n : 0);
+  };
+  auto stash = [&](__nv_bfloat16* dst, const Row16& r) {
+    uint4* d = reinterpret_cast<uint4*>(dst + lrow * kLd + lseg);
+    d[0] = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]);
+    d[1] = make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]);
+  };
+  const int wm = warp & 3, wn = warp >> 2;
+  float acc[4][4] = {};
+  Row16 ra = fetch_a(kbeg), rb = fetch_b(kbeg);
+  stash(As[0], ra);
+  stash(Bs[0], rb);
+  __syncthreads();
+  int cur = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += kTile) {
+    const bool more = k0 + kTile < kend;
+    if (more) {
+      ra = fetch_a(k0 + kTile);
+      rb = fetch_b(k0 + kTile);
+    }
+    const __nv_bfloat16* at = As[cur];
+    const __nv_bfloat16* bt = Bs[cur];
+#pragma unroll
+    for (int ks = 0; ks < kTile / 16; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      if (AK)
+        ldsm_x4(smem_u32(at + (wm * 16 + (lane & 15)) * kLd + ks * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
+      else
+        ldsm_x4_trans(smem_u32(at + (ks * 16 + (lane & 7) + ((lane >> 4) << 3)) * kLd + wm * 16 +
+                               ((lane >> 3) & 1) * 8),
+                      a0, a1, a2, a3);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        if (BK)
+          ldsm_x4(smem_u32(bt + (wn * 32 + np * 16 + (lane & 7) + ((lane >> 4) << 3)) * kLd + ks * 16 +
+                           ((lane >> 3) & 1) * 8),
+                  b0, b1, b2, b3);
+        else
+          ldsm_x4_trans(smem_u32(bt + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kLd + wn * 32 +
+                                 np * 16 + ((lane >> 4) << 3)),
+                        b0, b1, b2, b3);
+        mma_bf16(acc[2 * np], a0, a1, a2, a3, b0, b1);
+        mma_bf16(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    if (more) {
+      stash(As[cur ^ 1], ra);
+      stash(Bs[cur ^ 1], rb);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gm = m0 + wm * 16 + g + (e >> 1) * 8;
+      const int gn = n0 + wn * 32 + nt * 8 + 2 * t + (e & 1);
+      if (gm >= M || gn >= N) continue;
+      float* dst = c + gm * ldc + gn;
+      if (gridDim.z > 1) atomicAdd(dst, acc[nt][e]); else *dst = acc[nt][e];
+    }
+}
+
+template <typename TA, typename TB, bool AK, bool BK>
+int launch_gemm(const TA* a, long long lda, const TB* b, long long ldb, float* c, long long ldc, int M,
+                int N, int K, cudaStream_t s) {
+  const int tiles = ((M + kTile - 1) / kTile) * ((N + kTile - 1) / kTile);
   int splits = 1;
   if (tiles < 148 && K >= 1024) {
     splits = (296 + tiles - 1) / tiles;
@@ -81,11 +185,11 @@ int launch_gemm(const TA* a, long long sam, long long sak, const TB* b, long lon
     if (splits < 1) splits = 1;
   }
   int kps = (K + splits - 1) / splits;
-  kps = (kps + TK - 1) / TK * TK;
+  kps = (kps + kTile - 1) / kTile * kTile;
   splits = (K + kps - 1) / kps;
   if (splits > 1) cudaMemsetAsync(c, 0, sizeof(float) * static_cast<size_t>(M) * ldc, s);
-  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
-  gemm_simt_kernel<TA, TB><<<grid, 256, 0, s>>>(a, sam, sak, b, sbn, sbk, c, ldc, M, N, K, kps);
+  dim3 grid((N + kTile - 1) / kTile, (M + kTile - 1) / kTile, splits);
+  gemm_mma_kernel<TA, TB, AK, BK><<<grid, 256, 0, s>>>(a, lda, b, ldb, c, ldc, M, N, K, kps);
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
 
@@ -141,8 +245,8 @@ __global__ void dhead_tail_bwd_kernel(const float* __restrict__ h, const float* 
 int dhead_forward(const __nv_bfloat16* x_flat, const float* w0, const float* b0, const float* w2,
                   const float* b2, float slope, float* h, float* p, int B, int fc_in, int fc_mid,
                   cudaStream_t s) {
-  if (int rc = launch_gemm<__nv_bfloat16, float>(x_flat, fc_in, 1, w0, fc_in, 1, h, fc_mid, B, fc_mid,
-                                                 fc_in, s))
+  if (int rc = launch_gemm<__nv_bfloat16, float, true, true>(x_flat, fc_in, w0, fc_in, h, fc_mid, B, fc_mid,
+                                                             fc_in, s))
     return rc;
   dhead_tail_fwd_kernel<<<B, 256, 0, s>>>(h, b0, w2, b2, slope, p, fc_mid);
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
@@ -158,14 +262,14 @@ int dhead_backward(const __nv_bfloat16* x_flat, const float* w0, const float* w2
   dhead_tail_bwd_kernel<<<B, 256, 0, s>>>(h, w2, p, dp, slope, dh, dw2, db2, db0, fc_mid);
   if (need_wgrad) {
     // dW0[m=fc_mid, n=fc_in] = sum_b dh[b,m] * x[b,n]
-    if (int rc = launch_gemm<float, __nv_bfloat16>(dh, 1, fc_mid, x_flat, 1, fc_in, dw0, fc_in, fc_mid,
-                                                   fc_in, B, s))
+    if (int rc = launch_gemm<float, __nv_bfloat16, false, false>(dh, fc_mid, x_flat, fc_in, dw0, fc_in, fc_mid,
+                                                               fc_in, B, s))
       return rc;
   }
   if (dx_flat) {
     // dx[b, n=fc_in] = sum_k dh[b,k] * W0[k,n]
-    if (int rc = launch_gemm<float, float>(dh, fc_mid, 1, w0, 1, fc_in, dx_flat, fc_in, B, fc_in,
-                                           fc_mid, s))
+    if (int rc = launch_gemm<float, float, true, false>(dh, fc_mid, w0, fc_in, dx_flat, fc_in, B, fc_in,
+                                                       fc_mid, s))
       return rc;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 4;

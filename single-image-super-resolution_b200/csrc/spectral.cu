@@ -154,10 +154,11 @@ __device__ __forceinline__ int find_layer(const int* __restrict__ begin, int n, 
 
 // t[k] = sum_co W[co,k] u[co] for a 128-column chunk of one layer (training layers only)
 __global__ void __launch_bounds__(256)
-sn_batched_wtu_kernel(const SnLayer* __restrict__ tab, const int* __restrict__ blk_begin, int n_layers) {
+sn_batched_wtu_kernel(const __grid_constant__ SnTable tab) {
   __shared__ float part[128];
-  const int l = find_layer(blk_begin, n_layers, blockIdx.x);
-  const SnLayer L = tab[l];
+  const int* blk_begin = tab.wtu_begin;
+  const int l = find_layer(blk_begin, tab.n, blockIdx.x);
+  const SnLayer& L = tab.L[l];
   if (!L.training) return;
   const int k = (blockIdx.x - blk_begin[l]) * 128 + (threadIdx.x & 127);
   const int half = threadIdx.x >> 7;
@@ -172,10 +173,11 @@ sn_batched_wtu_kernel(const SnLayer* __restrict__ tab, const int* __restrict__ b
 }
 // s_raw[co] = sum_k W[co,k] * (training ? t[k] : v[k]); one block per (layer, row)
 __global__ void __launch_bounds__(128)
-sn_batched_wv_kernel(const SnLayer* __restrict__ tab, const int* __restrict__ row_begin, int n_layers) {
+sn_batched_wv_kernel(const __grid_constant__ SnTable tab) {
   __shared__ float scratch[32];
-  const int l = find_layer(row_begin, n_layers, blockIdx.x);
-  const SnLayer L = tab[l];
+  const int* row_begin = tab.row_begin;
+  const int l = find_layer(row_begin, tab.n, blockIdx.x);
+  const SnLayer& L = tab.L[l];
   const int co = blockIdx.x - row_begin[l];
   const float* vec = L.training ? L.t : L.v;
   const float* wr = L.w + static_cast<size_t>(co) * L.K;
@@ -186,9 +188,9 @@ sn_batched_wv_kernel(const SnLayer* __restrict__ tab, const int* __restrict__ ro
 }
 // per layer: normalise, write u/v (training), sigma, and the copies kept for backward
 __global__ void __launch_bounds__(256)
-sn_batched_finish_kernel(const SnLayer* __restrict__ tab, float eps) {
+sn_batched_finish_kernel(const __grid_constant__ SnTable tab, float eps) {
   __shared__ float scratch[32];
-  const SnLayer L = tab[blockIdx.x];
+  const SnLayer& L = tab.L[blockIdx.x];
   if (L.training) {
     float a = 0.f;
     for (int k = threadIdx.x; k < L.K; k += blockDim.x) a += L.t[k] * L.t[k];
@@ -225,10 +227,10 @@ sn_batched_finish_kernel(const SnLayer* __restrict__ tab, float eps) {
 
 // weight_prep for every conv of a network; block -> (layer, chunk of 1024 elements)
 __global__ void __launch_bounds__(256)
-weight_prep_batched_kernel(const PrepLayer* __restrict__ tab, const int* __restrict__ blk_begin,
-                           int n_layers) {
-  const int l = find_layer(blk_begin, n_layers, blockIdx.x);
-  const PrepLayer L = tab[l];
+weight_prep_batched_kernel(const __grid_constant__ PrepTable tab) {
+  const int* blk_begin = tab.blk_begin;
+  const int l = find_layer(blk_begin, tab.n, blockIdx.x);
+  const PrepLayer& L = tab.L[l];
   const float inv = L.sigma ? 1.f / *L.sigma : 1.f;
   const int taps = L.k * L.k;
   const long long total = static_cast<long long>(L.cout) * taps * L.cin;
@@ -276,21 +278,42 @@ int sn_power_iteration(const float* w, float* u, float* v, float* sigma, int Cou
   return check();
 }
 
-int sn_power_iteration_batched(const SnLayer* tab_dev, const int* wtu_begin_dev, const int* row_begin_dev,
-                               int n_layers, int total_wtu_blocks, int total_rows, float eps,
-                               cudaStream_t s) {
-  if (n_layers == 0) return 0;
-  if (total_wtu_blocks > 0)
-    sn_batched_wtu_kernel<<<total_wtu_blocks, 256, 0, s>>>(tab_dev, wtu_begin_dev, n_layers);
-  sn_batched_wv_kernel<<<total_rows, 128, 0, s>>>(tab_dev, row_begin_dev, n_layers);
-  sn_batched_finish_kernel<<<n_layers, 256, 0, s>>>(tab_dev, eps);
+int sn_power_iteration_batched(const SnLayer* layers, int n_layers, float eps, cudaStream_t s) {
+  for (int base = 0; base < n_layers; base += kMaxBatch) {
+    SnTable tab;
+    tab.n = n_layers - base < kMaxBatch ? n_layers - base : kMaxBatch;
+    int wtu = 0, rows = 0;
+    for (int i = 0; i < tab.n; ++i) {
+      tab.L[i] = layers[base + i];
+      tab.wtu_begin[i] = wtu;
+      tab.row_begin[i] = rows;
+      if (tab.L[i].training) wtu += (tab.L[i].K + 127) / 128;
+      rows += tab.L[i].cout;
+    }
+    tab.wtu_begin[tab.n] = wtu;
+    tab.row_begin[tab.n] = rows;
+    if (wtu > 0) sn_batched_wtu_kernel<<<wtu, 256, 0, s>>>(tab);
+    sn_batched_wv_kernel<<<rows, 128, 0, s>>>(tab);
+    sn_batched_finish_kernel<<<tab.n, 256, 0, s>>>(tab, eps);
+  }
   return check();
 }
 
-int weight_prep_batched(const PrepLayer* tab_dev, const int* blk_begin_dev, int n_layers,
-                        int total_blocks, cudaStream_t s) {
-  if (n_layers == 0 || total_blocks == 0) return 0;
-  weight_prep_batched_kernel<<<total_blocks, 256, 0, s>>>(tab_dev, blk_begin_dev, n_layers);
+int weight_prep_batched(const PrepLayer* layers, int n_layers, cudaStream_t s) {
+  for (int base = 0; base < n_layers; base += kMaxBatch) {
+    PrepTable tab;
+    tab.n = n_layers - base < kMaxBatch ? n_layers - base : kMaxBatch;
+    int blocks = 0;
+    for (int i = 0; i < tab.n; ++i) {
+      tab.L[i] = layers[base + i];
+      if (tab.L[i].ps_r > 1 && tab.L[i].cout % (tab.L[i].ps_r * tab.L[i].ps_r)) return 1;
+      tab.blk_begin[i] = blocks;
+      const long long total = static_cast<long long>(tab.L[i].cout) * tab.L[i].cin * tab.L[i].k * tab.L[i].k;
+      blocks += static_cast<int>((total + 1023) / 1024);
+    }
+    tab.blk_begin[tab.n] = blocks;
+    if (blocks > 0) weight_prep_batched_kernel<<<blocks, 256, 0, s>>>(tab);
+  }
   return check();
 }
 

@@ -6,7 +6,8 @@
 
 namespace sisr {
 
-// Device-resident per-layer descriptors of the batched (one launch per network) variants.
+// Per-layer descriptors of the batched (one launch chain per network) variants; same layout as
+// sisr_sn_layer / sisr_prep_layer of the C ABI.
 struct SnLayer {
   const float* w;      // [cout, K] fp32 master weight
   float* u;            // [cout]  module buffer (updated in training)
@@ -28,12 +29,24 @@ struct PrepLayer {
   int cout, cin, k, ps_r;
 };
 
+// Tables travel as kernel parameters (no device-side table, CUDA-graph safe).
+constexpr int kMaxBatch = 40;
+struct SnTable {
+  SnLayer L[kMaxBatch];
+  int wtu_begin[kMaxBatch + 1];   // first 128-column block of each layer (training layers only)
+  int row_begin[kMaxBatch + 1];   // first weight row of each layer
+  int n;
+};
+struct PrepTable {
+  PrepLayer L[kMaxBatch];
+  int blk_begin[kMaxBatch + 1];   // first 1024-element block of each layer
+  int n;
+};
+
 size_t sn_workspace_floats(int Cout, int K);
-int sn_power_iteration_batched(const SnLayer* tab_dev, const int* wtu_begin_dev, const int* row_begin_dev,
-                               int n_layers, int total_wtu_blocks, int total_rows, float eps,
-                               cudaStream_t s);
-int weight_prep_batched(const PrepLayer* tab_dev, const int* blk_begin_dev, int n_layers,
-                        int total_blocks, cudaStream_t s);
+// `layers` are HOST arrays; one launch chain per <= kMaxBatch layers
+int sn_power_iteration_batched(const SnLayer* layers, int n_layers, float eps, cudaStream_t s);
+int weight_prep_batched(const PrepLayer* layers, int n_layers, cudaStream_t s);
 // w: [Cout, K] fp32 (K = Cin*kh*kw, native flatten order).  training: one power iteration,
 // u/v updated in place, sigma written.  eval: sigma = u^T W v with the stored vectors.
 int sn_power_iteration(const float* w, float* u, float* v, float* sigma, int Cout, int K,

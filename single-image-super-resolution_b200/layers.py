@@ -45,7 +45,8 @@ class SNConv2d(nn.Module):
         else:
             self.weight = nn.Parameter(w)
             self.bias = nn.Parameter(b)
-        self._prep_cache = None
+        self._prep = None
+        self.ps_r = 0          # 2 when a PixelShuffle(2) follows (set by the owning stage)
 
     @property
     def master_weight(self) -> torch.Tensor:
@@ -58,7 +59,8 @@ class SNConv2d(nn.Module):
                       want_stats=want_stats, training=self.training, out_nchw_f32=out_nchw_f32)
         u = self.weight_u if self.sn else None
         v = self.weight_v if self.sn else None
-        return Conv2dFn.apply(x, self.master_weight, self.bias, u, v, slope, cfg)
+        prep, self._prep = self._prep, None      # set by ops.prepare_convs for exactly one forward
+        return Conv2dFn.apply(x, self.master_weight, self.bias, u, v, slope, cfg, prep)
 
     def forward(self, x):  # module-boundary use: NCHW fp32 in / out
         y, _ = self.run(ops.ToNHWC.apply(x))

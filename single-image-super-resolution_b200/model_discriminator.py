@@ -55,6 +55,7 @@ class Discriminator(nn.Module):
             nn.Sigmoid())
 
     def forward(self, x):
+        ops.prepare_convs([self.conv[0]] + [b.layers[0] for b in self.conv[2]], x.requires_grad)
         x = ops.ToNHWC.apply(x)
         x, _ = self.conv[0].run(x, act=ACT_LEAKY)
         for block in self.conv[2]:

@@ -51,6 +51,7 @@ class _UpscaleStage(nn.Sequential):
             raise NotImplementedError("only PixelShuffle(2) stages are built (the reference's "
                                       "config.py uses list_scales = [2])")
         super().__init__(SNConv2d(cin, cout, 3, 1, 1, sn=sn), nn.PixelShuffle(scale), nn.PReLU())
+        self[0].ps_r = scale
 
     def forward_nhwc(self, x):
         y, _ = self[0].run(x, act=ACT_PRELU, slope=self[2].weight, ps_r=2)
@@ -113,6 +114,15 @@ class Generator(nn.Module):
             print("  - non utilisés :", len(unused), unused)
         return result
 
+    def convs_no_end(self):
+        """The SNConv2d modules in forward order (without the output conv)."""
+        convs = [self.first_layers[0]]
+        for block in self.block_list:
+            convs += [block.layers[0], block.layers[3]]
+        convs.append(self.block_list_end[0])
+        convs += [stage[0] for stage in self.upscale]
+        return convs
+
     def forward_no_end_nhwc(self, x):
         """x: NHWC bf16 LR image -> NHWC bf16 feature map after the upscale stages."""
         conv0, act0 = self.first_layers
@@ -128,9 +138,11 @@ class Generator(nn.Module):
         return x
 
     def forward_no_end(self, x):
+        ops.prepare_convs(self.convs_no_end(), x.requires_grad)
         return ops.ToNCHW.apply(self.forward_no_end_nhwc(ops.ToNHWC.apply(x)))
 
     def forward(self, x):
+        ops.prepare_convs(self.convs_no_end() + [self.end[0]], x.requires_grad)
         return self.end.forward_nhwc(self.forward_no_end_nhwc(ops.ToNHWC.apply(x)))
 
     def freeze(self, freeze_upscale=False, freeze_end=False):
@@ -167,11 +179,16 @@ class GeneratorSuffix(nn.Module):
             for p in self.upscale.parameters():
                 p.requires_grad = False
 
+    def convs_no_end(self):
+        return self.base.convs_no_end() + [self.upscale[0]]
+
     def forward_no_end_nhwc(self, x):
         return self.upscale.forward_nhwc(self.base.forward_no_end_nhwc(x))
 
     def forward_no_end(self, x):
+        ops.prepare_convs(self.convs_no_end(), x.requires_grad)
         return ops.ToNCHW.apply(self.forward_no_end_nhwc(ops.ToNHWC.apply(x)))
 
     def forward(self, x):
+        ops.prepare_convs(self.convs_no_end() + [self.end[0][0]], x.requires_grad)
         return self.end[0].forward_nhwc(self.forward_no_end_nhwc(ops.ToNHWC.apply(x)))

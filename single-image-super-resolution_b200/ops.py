@@ -7,6 +7,7 @@ parameters are fp32.  PyTorch supplies device memory, streams and the autograd t
 from __future__ import annotations
 
 import contextlib
+import ctypes
 from dataclasses import dataclass
 from typing import Optional
 
@@ -22,6 +23,9 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 _skip_param_grads = False
+# {data_ptr of a gradient tensor: (that tensor, its per-channel column sums)}: lets the kernel that
+# writes a conv's output gradient also deliver the conv's bias gradient (cleared every step)
+_colsum_cache = {}
 
 
 @contextlib.contextmanager
@@ -110,6 +114,98 @@ class ToNCHW(torch.autograd.Function):
         return gx
 
 
+# ----------------------------------------------------------------------------- batched weight preparation
+class _SnLayerC(ctypes.Structure):
+    """struct sisr_sn_layer"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w", "u", "v", "t", "s", "sigma", "u_saved", "v_saved")] + \
+               [(n, ctypes.c_int) for n in ("cout", "k", "training", "reserved")]
+
+
+class _PrepLayerC(ctypes.Structure):
+    """struct sisr_prep_layer"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w", "sigma", "bias", "wf", "wd", "bias_perm")] + \
+               [(n, ctypes.c_int) for n in ("cout", "cin", "k", "ps_r")]
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def prepare_convs(convs, first_needs_dx: bool):
+    """Spectral-norm power iteration + bf16 weight re-layout for every conv of a network in one
+    launch chain (3 + 1 kernels instead of 4 per layer).  ``convs``: the network's ``SNConv2d``
+    modules in forward order.  Each module receives ``_prep`` = (wf, wd, sigma, u_saved, v_saved,
+    bias_used), consumed by its next ``run``.  All outputs of one call live in two fresh buffers, so
+    that several forward calls before a backward (the three discriminator passes of a step) keep
+    their own sigma / weights, as the reference's per-call power iteration requires."""
+    if not convs:
+        return
+    dev = convs[0].master_weight.device
+    _require_cuda(convs[0].master_weight, "prepare_convs")
+    st = _stream()
+    f_off, h_off, plan = 0, 0, []
+    for i, c in enumerate(convs):
+        w = c.master_weight
+        cout, cin, k, _ = w.shape
+        K = cin * k * k
+        need_dx = first_needs_dx or i > 0
+        e = {"conv": c, "cout": cout, "cin": cin, "k": k, "K": K, "ps_r": getattr(c, "ps_r", 0)}
+        if c.sn:
+            for name, n in (("sigma", 4), ("t", K), ("s", cout), ("u_saved", cout), ("v_saved", K)):
+                e[name] = (f_off, n)
+                f_off += _round_up(n, 4)
+        if e["ps_r"] == 2:
+            e["bias_perm"] = (f_off, cout)
+            f_off += _round_up(cout, 4)
+        e["wf"] = (h_off, cout * K)
+        h_off += _round_up(cout * K, 64)
+        if need_dx:
+            e["wd"] = (h_off, cout * K)
+            h_off += _round_up(cout * K, 64)
+        plan.append(e)
+    fbuf = torch.empty(max(f_off, 4), dtype=torch.float32, device=dev)
+    hbuf = torch.empty(max(h_off, 64), dtype=torch.bfloat16, device=dev)
+
+    def fv(e, name):
+        if name not in e:
+            return None
+        o, n = e[name]
+        return fbuf[o:o + n]
+
+    sn_rows, prep_rows = [], []
+    for e in plan:
+        c = e["conv"]
+        w = c.master_weight
+        cout, cin, k = e["cout"], e["cin"], e["k"]
+        sigma = None
+        if c.sn:
+            sigma = fv(e, "sigma")[:1]
+            sn_rows.append(_SnLayerC(w.data_ptr(), c.weight_u.data_ptr(), c.weight_v.data_ptr(),
+                                     fv(e, "t").data_ptr(), fv(e, "s").data_ptr(), sigma.data_ptr(),
+                                     fv(e, "u_saved").data_ptr(), fv(e, "v_saved").data_ptr(),
+                                     cout, e["K"], 1 if c.training else 0, 0))
+        o, n = e["wf"]
+        wf = hbuf[o:o + n].view(cout, k, k, cin)
+        wd = None
+        if "wd" in e:
+            o, n = e["wd"]
+            wd = hbuf[o:o + n].view(cin, k, k, cout)
+        bias_perm = fv(e, "bias_perm")
+        prep_rows.append(_PrepLayerC(w.data_ptr(), sigma.data_ptr() if sigma is not None else None,
+                                     c.bias.data_ptr(), wf.data_ptr(), wd.data_ptr() if wd is not None else None,
+                                     bias_perm.data_ptr() if bias_perm is not None else None,
+                                     cout, cin, k, e["ps_r"]))
+        c._prep = (wf, wd, sigma, fv(e, "u_saved"), fv(e, "v_saved"),
+                   bias_perm if bias_perm is not None else c.bias)
+    if sn_rows:
+        arr = (_SnLayerC * len(sn_rows))(*sn_rows)
+        _lib.LAUNCHES[0] += 3 * ((len(sn_rows) + 39) // 40) - 1
+        call("sisr_sn_power_iteration_batched", ctypes.addressof(arr), len(sn_rows), SN_EPS, st)
+    arr = (_PrepLayerC * len(prep_rows))(*prep_rows)
+    _lib.LAUNCHES[0] += (len(prep_rows) + 39) // 40 - 1
+    call("sisr_weight_prep_batched", ctypes.addressof(arr), len(prep_rows), st)
+
+
 # ----------------------------------------------------------------------------- convolution
 @dataclass(frozen=True)
 class ConvCfg:
@@ -143,17 +239,20 @@ class Conv2dFn(torch.autograd.Function):
         cout, cin, k, _ = weight.shape
         d = _desc(x.shape, cout, k, cfg)
         st = _stream()
-        sigma = None
-        if u is not None:
+        sigma = saved_u = saved_v = None
+        if u is not None and (prepared is None or len(prepared) == 2):
             sigma = torch.empty(1, dtype=torch.float32, device=dev)
             ws = torch.empty(query("sisr_sn_workspace_floats", cout, cin * k * k), dtype=torch.float32,
                              device=dev)
             call("sisr_sn_power_iteration", weight, u, v, sigma, cout, cin * k * k,
                  1 if cfg.training else 0, SN_EPS, ws, st)
+            saved_u, saved_v = u.clone(), v.clone()
         need_dx = x.requires_grad
         bias_used = bias
-        if prepared is not None:       # frozen weights prepared once by the caller (MaskedVGG)
+        if prepared is not None and len(prepared) == 2:   # frozen weights prepared once (MaskedVGG)
             wf, wd = prepared
+        elif prepared is not None:                         # ops.prepare_convs (whole network at once)
+            wf, wd, sigma, saved_u, saved_v, bias_used = prepared
         else:
             wf = torch.empty((cout, k, k, cin), dtype=torch.bfloat16, device=dev)
             wd = torch.empty((cin, k, k, cout), dtype=torch.bfloat16, device=dev) if need_dx else None
@@ -175,8 +274,6 @@ class Conv2dFn(torch.autograd.Function):
         ctx.has_sn = u is not None
         ctx.has_slope = slope is not None
         ctx.skip_params = _skip_param_grads
-        saved_u = u.clone() if u is not None else None
-        saved_v = v.clone() if v is not None else None
         ctx.save_for_backward(x, weight, wf, wd, y if cfg.act != ACT_NONE else None, sigma, saved_u,
                               saved_v, slope)
         if stats is not None:
@@ -191,7 +288,7 @@ class Conv2dFn(torch.autograd.Function):
         st = _stream()
         cout, cin, k, _ = weight.shape
         gy = gy.contiguous()
-        dslope = None
+        dslope = colsum = None
         if cfg.out_nchw_f32:
             dpre = torch.empty((d.n, d.oh, d.ow, cout), dtype=torch.bfloat16, device=dev)
             if cfg.act == ACT_TANH:
@@ -201,11 +298,19 @@ class Conv2dFn(torch.autograd.Function):
         elif cfg.act != ACT_NONE:
             dpre = torch.empty_like(gy)
             want_ds = cfg.act == ACT_PRELU and ctx.needs_input_grad[5] and not ctx.skip_params
-            if want_ds:
-                dslope = torch.zeros(1, dtype=torch.float32, device=dev)
-            call("sisr_act_bwd", gy, y, cfg.act, cfg.leaky_slope, slope, dpre, dslope, gy.numel(), st)
+            want_db = ctx.needs_input_grad[2] and not ctx.skip_params and cfg.ps_r != 2
+            c_last = gy.shape[-1]
+            if want_ds or want_db:
+                zbuf = torch.zeros(1 + c_last, dtype=torch.float32, device=dev)
+                dslope = zbuf[:1] if want_ds else None
+                colsum = zbuf[1:] if want_db else None
+            call("sisr_act_bwd", gy, y, cfg.act, cfg.leaky_slope, slope, dpre, dslope, colsum,
+                 gy.numel() // c_last, c_last, st)
         else:
             dpre = gy
+            hit = _colsum_cache.pop(gy.data_ptr(), None)
+            if hit is not None and hit[0].numel() == gy.numel() and cfg.ps_r != 2:
+                colsum = hit[1]
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -216,7 +321,9 @@ class Conv2dFn(torch.autograd.Function):
             dbp = torch.empty(cout, dtype=torch.float32, device=dev)
             nbytes = query("sisr_conv_wgrad_workspace_bytes", d)
             ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dev)
-            call("sisr_conv_wgrad", d, x, dpre, gp, dbp, ws, st)
+            call("sisr_conv_wgrad", d, x, dpre, gp, dbp if colsum is None else None, ws, st)
+            if colsum is not None:      # bias gradient already reduced by the kernel that wrote dpre
+                dbp = colsum
             dw = torch.empty_like(weight)
             db = torch.empty(cout, dtype=torch.float32, device=dev)
             ws2 = torch.empty(4, dtype=torch.float32, device=dev)
@@ -285,7 +392,9 @@ class BnActFn(torch.autograd.Function):
         rows = y.numel() // c
         st = _stream()
         gout = gout.contiguous()
-        sums = torch.zeros(2 * c + 1, dtype=torch.float32, device=dev)
+        zbuf = torch.zeros(3 * c + 1, dtype=torch.float32, device=dev)
+        sums = zbuf[:2 * c + 1]
+        colsum = zbuf[2 * c + 1:] if not ctx.skip_params else None
         call("sisr_bn_bwd_reduce", gout, y, aux[2], aux[3], aux[0], aux[1], cfg.act, cfg.leaky_slope,
              slope, sums, rows, c, st)
         local = sums
@@ -300,7 +409,10 @@ class BnActFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dy = torch.empty_like(y)
             call("sisr_bn_bwd_apply", gout, y, aux[2], aux[3], aux[0], aux[1], cfg.act, cfg.leaky_slope,
-                 slope, red, ctx.count, dy, rows, c, st)
+                 slope, red, ctx.count, dy, colsum, rows, c, st)
+            if colsum is not None:
+                # per-channel sum of dy = bias gradient of the producing conv; handed to its backward
+                _colsum_cache[dy.data_ptr()] = (dy, colsum)
         dgamma = dbeta = dslope = None
         if not ctx.skip_params:
             if ctx.needs_input_grad[2]:

@@ -244,9 +244,11 @@ def test_train_step_gradients_and_update_vs_oracle(cuda):
         gj = S.generator_state(seed, n_blocks=2, n_suffix=1)
         dj = S.discriminator_state(seed + 1, shape, feats, strides)
         with O.emulate_bf16_storage(), O.jitter_before_rounding(1e-6, sd):
-            return O.train_step(gj, dj, S.vgg_state(seed + 2, mask), hr, lr_img, d_strides=strides,
-                                vgg_mask=mask, opt_g=O.AdamState(O.trainable_names(gj), lr),
-                                opt_d=O.AdamState(O.trainable_names(dj), lr))
+            res = O.train_step(gj, dj, S.vgg_state(seed + 2, mask), hr, lr_img, d_strides=strides,
+                               vgg_mask=mask, opt_g=O.AdamState(O.trainable_names(gj), lr),
+                               opt_d=O.AdamState(O.trainable_names(dj), lr))
+        res["g_after"] = gj
+        return res
     j1, j2 = jittered(1), jittered(2)
     g_grads = {k: p.grad for k, p in tr.net_g.named_parameters()}
     d_grads = {k: p.grad for k, p in tr.net_d.named_parameters()}
@@ -260,13 +262,17 @@ def test_train_step_gradients_and_update_vs_oracle(cuda):
                 err = rel(mine[k], r)
                 assert err < max(8e-2, 1.5 * floor), (tag, k, err, floor)
                 assert cos(mine[k], r) > 0.8, (tag, k)
-    # Adam moved the trainable weights the same way (sign-like first step)
-    moved_same = []
+    # Adam moved the trainable weights the same way (the first step is sign-like, so the measure is
+    # the share of elements that moved in the same direction, against the share on which two
+    # jittered CPU runs of the same step agree with each other)
+    g_init = S.generator_state(seed, n_blocks=2, n_suffix=1)
     for k in ("base.end.0.weight_orig", "upscale.0.weight_orig", "base.block_list.1.layers.3.weight_orig"):
         mine = tr.net_g.state_dict()[k].cpu() - g_before[k].cpu()
-        want = g_st[k] - S.generator_state(seed, n_blocks=2, n_suffix=1)[k]
-        moved_same.append(float((torch.sign(mine) == torch.sign(want)).float().mean()))
-    assert min(moved_same) > 0.9, moved_same
+        want = g_st[k] - g_init[k]
+        same = float((torch.sign(mine) == torch.sign(want)).float().mean())
+        floor = float((torch.sign(j1["g_after"][k] - g_init[k]) ==
+                       torch.sign(j2["g_after"][k] - g_init[k])).float().mean())
+        assert same > min(0.9, floor - 0.05), (k, same, floor)
 
 
 def test_frozen_prefix_trains_only_the_suffix(cuda):
