@@ -277,7 +277,8 @@ def discriminator_forward(st: State, x: torch.Tensor, strides: Sequence[int],
         x = _q(conv(st, q + "0.", x, strides[k + 1], 1, training))
         x = _q(leaky(batch_norm(st, q + "1.", x, training)))
     x = x.reshape(b, -1)  # NCHW (c, h, w) order
-    x = leaky(F.linear(x, st["fc.0.weight"], st["fc.0.bias"]))
+    # the CUDA head feeds its three GEMMs bf16 operands (weight and dh rounded in flight)
+    x = leaky(_qg(F.linear(x, _qw(st["fc.0.weight"]), st["fc.0.bias"])))
     x = F.linear(x, st["fc.2.weight"], st["fc.2.bias"])
     return torch.sigmoid(x)
 

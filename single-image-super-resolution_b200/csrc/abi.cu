@@ -45,7 +45,7 @@ bool desc_ok(const sisr_conv_desc* d) {
 }
 bool tc_shape(const sisr_conv_desc* d) {
   return d->k == 3 && d->pad == 1 && (d->stride == 1 || d->stride == 2) && d->cin % 64 == 0 &&
-         d->cout % 64 == 0 && (d->ps_r < 2 || (d->stride == 1 && (d->cout / 4) % 32 == 0));
+         d->cout % 64 == 0 && d->cin <= 512 && d->cout <= 512 && (d->ps_r < 2 || (d->stride == 1 && (d->cout / 4) % 32 == 0));
 }
 // thin (3-channel) edge layers: stride 1, same-size
 bool thin_geometry(const sisr_conv_desc* d) {

@@ -4,7 +4,10 @@
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
 //   warps 2..5  : epilogue (tcgen05.ld -> bias / activation / BN statistics -> bf16 NHWC store)
 //
-// One CTA computes one 128 x BN output tile; the K loop runs over (tap, 64-channel block).
+// Persistent: one CTA per SM walks the 128 x BN output tiles (tile = blockIdx.x + i * gridDim.x);
+// the K loop of a tile runs over (tap, 64-channel block).  The TMEM accumulator is double
+// buffered (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and
+// barrier / TMEM set-up is paid once per SM instead of once per tile.
 // A tile : 128 pixels x 64 channels bf16 = 16 KB, 128 B rows, hardware 128 B swizzle (K-major).
 // B tile : BN rows x 64 k bf16, same layout.  Accumulator: 128 lanes x BN fp32 columns in TMEM.
 #include <stdio.h>
@@ -22,9 +25,11 @@ constexpr int kBK = 64;
 constexpr int kThreads = 192;
 constexpr int kATileBytes = kBM * kBK * 2;
 
+constexpr int kMaxCout = 512;   // per-CTA BN statistics accumulator
+
 struct KParams {
   int M, GH, GW, trav_stride, lower_w, lower_h;
-  int cin_blocks, num_taps, n_tiles;
+  int cin_blocks, num_taps, n_tiles, m_tiles;
   IgemmTaps taps;
   __nv_bfloat16* out;
   int OH, OW, ldc, osy, osx, opy, opx, ps_c;
@@ -70,18 +75,17 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                              ~static_cast<uintptr_t>(1023));
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_bias[BN];
-  __shared__ float s_stats[2 * BN];
+  __shared__ float s_stats[2 * kMaxCout];
+  __shared__ float s_bias[kMaxCout];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x % p.n_tiles;
-  const int tile_m = blockIdx.x / p.n_tiles;
-  const int m0 = tile_m * kBM;
-  const int n0 = tile_n * BN;
+  const int num_tiles = p.m_tiles * p.n_tiles;
   const int num_kb = p.num_taps * p.cin_blocks;
+  const int cout = p.n_tiles * BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -90,17 +94,20 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&tmem_full_bar), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 4);   // one arrival per epilogue warp
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_slot), BN);
+    tmem_alloc(smem_u32(&tmem_base_slot), 2 * BN);
     tmem_relinquish();
   }
   if (warp >= 2) {
-    const int t = threadIdx.x - 64;
-    for (int i = t; i < BN; i += 128) s_bias[i] = p.bias ? p.bias[n0 + i] : 0.f;
-    for (int i = t; i < 2 * BN; i += 128) s_stats[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < cout; i += 128) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (p.stats)
+      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) s_stats[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -111,130 +118,149 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const int hw = p.GH * p.GW;
-      const int n_img = m0 / hw;
-      const int rem = m0 - n_img * hw;
-      const int gh = rem / p.GW;
-      const int gw = rem - gh * p.GW;
-      const int cw = gw * p.trav_stride + p.lower_w;
-      const int ch = gh * p.trav_stride + p.lower_h;
-      int kb = 0;
-      for (int tap = 0; tap < p.num_taps; ++tap) {
-        for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
-          const int s = kb % STAGES;
-          const uint32_t round = kb / STAGES;
-          mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, L::kStageBytes);
-          const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
-          const uint32_t b_dst = a_dst + kATileBytes;
-          tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * kBK, cw, ch, n_img, p.taps.off_w[tap],
-                             p.taps.off_h[tap]);
-          tma_load_2d(b_dst, &tmap_b, fb, p.taps.k_off[tap] + cb * kBK, n0);
+      uint32_t kbg = 0;   // k-block counter across tiles (pipeline stage / phase)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * kBM;
+        const int n0 = (tile % p.n_tiles) * BN;
+        const int n_img = m0 / hw;
+        const int rem = m0 - n_img * hw;
+        const int gh = rem / p.GW;
+        const int gw = rem - gh * p.GW;
+        const int cw = gw * p.trav_stride + p.lower_w;
+        const int ch = gh * p.trav_stride + p.lower_h;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          for (int cb = 0; cb < p.cin_blocks; ++cb, ++kbg) {
+            const uint32_t s = kbg % STAGES;
+            const uint32_t round = kbg / STAGES;
+            mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            mbar_expect_tx(fb, L::kStageBytes);
+            const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
+            const uint32_t b_dst = a_dst + kATileBytes;
+            tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * kBK, cw, ch, n_img, p.taps.off_w[tap],
+                               p.taps.off_h[tap]);
+            tma_load_2d(b_dst, &tmap_b, fb, p.taps.k_off[tap] + cb * kBK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t round = kb / STAGES;
-      mbar_wait(smem_u32(&full_bar[s]), round & 1);
+    uint32_t kbg = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, use = it >> 1;
+      mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1) ^ 1);   // epilogue drained this buffer
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + kATileBytes;
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+        const uint32_t s = kbg % STAGES;
+        const uint32_t round = kbg / STAGES;
+        mbar_wait(smem_u32(&full_bar[s]), round & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+          if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
         }
-        umma_commit(smem_u32(&empty_bar[s]));
-        if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full_bar));
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row = m0 + quad * 32 + lane;
-    const bool valid = row < p.M;
     const int hw = p.GH * p.GW;
-    const int rr = valid ? row : 0;
-    const int n_img = rr / hw;
-    const int rem = rr - n_img * hw;
-    const int gh = rem / p.GW;
-    const int gw = rem - gh * p.GW;
     float slope = p.slope;
     if (p.act == ACT_PRELU) slope = __ldg(p.slope_ptr);
     if (p.act == ACT_RELU) slope = 0.f;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, use = it >> 1;
+      const int m0 = (tile / p.n_tiles) * kBM;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool valid = row < p.M;
+      const int rr = valid ? row : 0;
+      const int n_img = rr / hw;
+      const int rem = rr - n_img * hw;
+      const int gh = rem / p.GW;
+      const int gw = rem - gh * p.GW;
 
-    mbar_wait(smem_u32(&tmem_full_bar), 0);
-    tc_fence_after();
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
+      tc_fence_after();
 
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, raw);
-      tmem_ld_wait();
-      float v[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, raw);
+        tmem_ld_wait();
+        const int ncol = n0 + c * 32;
+        float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = __uint_as_float(raw[i]) + s_bias[c * 32 + i];
-        if (p.act != ACT_NONE) x = x > 0.f ? x : x * slope;
-        v[i] = x;
-      }
-      // destination of this 32-channel chunk
-      const int ncol = n0 + c * 32;
-      int oy, ox, ch;
-      if (p.ps_c > 0) {
-        const int sub = ncol / p.ps_c;
-        ch = ncol - sub * p.ps_c;
-        oy = gh * 2 + (sub >> 1);
-        ox = gw * 2 + (sub & 1);
-      } else {
-        ch = ncol;
-        oy = gh * p.osy + p.opy;
-        ox = gw * p.osx + p.opx;
-      }
-      uint32_t packed[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-      if (valid) {
-        __nv_bfloat16* dst =
-            p.out + (static_cast<size_t>(n_img * p.OH + oy) * p.OW + ox) * p.ldc + ch;
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-      }
-      if (p.stats) {
-        // statistics of the values as stored (bf16-rounded), invalid rows contribute zero
-        float q[32];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&packed[i]);
-          const float a = valid ? __low2float(h) : 0.f;
-          const float b = valid ? __high2float(h) : 0.f;
-          v[2 * i] = a;
-          v[2 * i + 1] = b;
-          q[2 * i] = a * a;
-          q[2 * i + 1] = b * b;
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(raw[i]) + s_bias[ncol + i];
+          if (p.act != ACT_NONE) x = x > 0.f ? x : x * slope;
+          v[i] = x;
         }
-        const float cs = column_sums_32x32(v, lane);
-        const float cq = column_sums_32x32(q, lane);
-        atomicAdd(&s_stats[c * 32 + lane], cs);
-        atomicAdd(&s_stats[BN + c * 32 + lane], cq);
+        // destination of this 32-channel chunk
+        int oy, ox, ch;
+        if (p.ps_c > 0) {
+          const int sub = ncol / p.ps_c;
+          ch = ncol - sub * p.ps_c;
+          oy = gh * 2 + (sub >> 1);
+          ox = gw * 2 + (sub & 1);
+        } else {
+          ch = ncol;
+          oy = gh * p.osy + p.opy;
+          ox = gw * p.osx + p.opx;
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        if (valid) {
+          __nv_bfloat16* dst =
+              p.out + (static_cast<size_t>(n_img * p.OH + oy) * p.OW + ox) * p.ldc + ch;
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+        if (p.stats) {
+          // statistics of the values as stored (bf16-rounded), invalid rows contribute zero
+          float q[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&packed[i]);
+            const float a = valid ? __low2float(h) : 0.f;
+            const float b = valid ? __high2float(h) : 0.f;
+            v[2 * i] = a;
+            v[2 * i + 1] = b;
+            q[2 * i] = a * a;
+            q[2 * i + 1] = b * b;
+          }
+          const float cs = column_sums_32x32(v, lane);
+          const float cq = column_sums_32x32(q, lane);
+          atomicAdd(&s_stats[ncol + lane], cs);
+          atomicAdd(&s_stats[cout + ncol + lane], cq);
+        }
       }
+      // this warp's TMEM reads of the buffer are complete: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
     }
     if (p.stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 64;
-      const int cout = p.n_tiles * BN;
-      for (int i = t; i < BN; i += 128) {
-        atomicAdd(&p.stats[n0 + i], s_stats[i]);
-        atomicAdd(&p.stats[cout + n0 + i], s_stats[BN + i]);
+      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) {
+        const float sv = s_stats[i];
+        if (sv != 0.f) atomicAdd(&p.stats[i], sv);
       }
     }
   }
@@ -243,7 +269,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -270,17 +296,37 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
   return 0;
 }
 
-int pick_bn(int m_tiles, int cout, int ps_c) {
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        g_num_sms <= 0)
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// Tile width: minimise waves x (MMA cycles of one tile + per-tile bubble); ties go to the wider
+// tile, which re-reads the activation operand fewer times.
+int pick_bn(int m_tiles, int cout, int ps_c, int num_kb) {
   const int cands[3] = {256, 128, 64};
+  long long best_cost = 0;
+  int best = 0;
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (cout % bn) continue;
     if (ps_c > 0 && (ps_c % 32)) continue;
-    if (bn == 64) return bn;
-    // keep at least ~2 CTAs per SM worth of tiles before growing the tile
-    if (static_cast<long long>(m_tiles) * (cout / bn) >= 296) return bn;
+    const long long tiles = static_cast<long long>(m_tiles) * (cout / bn);
+    const long long waves = (tiles + num_sms() - 1) / num_sms();
+    const long long cost = waves * (2LL * bn * num_kb + 300);
+    if (best == 0 || cost < best_cost) {
+      best = bn;
+      best_cost = cost;
+    }
   }
-  return 0;
+  return best;
 }
 
 }  // namespace
@@ -288,7 +334,7 @@ int pick_bn(int m_tiles, int cout, int ps_c) {
 const char* igemm_last_error() { return g_err; }
 
 bool igemm_supported(const IgemmProblem& p) {
-  if (p.Cin % 64 || p.Cout % 64) return false;
+  if (p.Cin % 64 || p.Cout % 64 || p.Cout > kMaxCout) return false;
   if (p.num_taps < 1 || p.num_taps > kMaxTaps) return false;
   if (p.ldc % 8) return false;
   if (p.ps_c > 0 && (p.ps_c % 32)) return false;
@@ -306,7 +352,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   }
   const long long M = static_cast<long long>(p.NB) * p.GH * p.GW;
   const int m_tiles = static_cast<int>((M + kBM - 1) / kBM);
-  const int bn = pick_bn(m_tiles, p.Cout, p.ps_c);
+  const int bn = pick_bn(m_tiles, p.Cout, p.ps_c, p.num_taps * (p.Cin / kBK));
   if (!bn) {
     snprintf(g_err, sizeof g_err, "igemm: no tile for Cout=%d", p.Cout);
     return 1;
@@ -331,6 +377,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.cin_blocks = p.Cin / kBK;
   kp.num_taps = p.num_taps;
   kp.n_tiles = p.Cout / bn;
+  kp.m_tiles = m_tiles;
   kp.taps = p.taps;
   kp.out = p.out;
   kp.OH = p.OH;
@@ -346,12 +393,13 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.slope = p.slope;
   kp.slope_ptr = p.slope_ptr;
   kp.stats = p.stats;
-  const int grid = m_tiles * kp.n_tiles;
+  const int tiles = m_tiles * kp.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
   switch (bn) {
     case 64:
-      return launch_variant<64, 4>(ta, tb, kp, grid, stream);
+      return launch_variant<64, 8>(ta, tb, kp, grid, stream);
     case 128:
-      return launch_variant<128, 3>(ta, tb, kp, grid, stream);
+      return launch_variant<128, 6>(ta, tb, kp, grid, stream);
     default:
       return launch_variant<256, 4>(ta, tb, kp, grid, stream);
   }

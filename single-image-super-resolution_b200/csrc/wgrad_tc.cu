@@ -169,13 +169,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
 }
 
-__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out,
-                                     long long total, int splits) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[k * total + i];
-    out[i] = s;
+// out[i] = sum_k ws[k][i]: block = 16 float4 columns x 16 split lanes, so that a thread issues at
+// most ceil(splits/16) independent 16-byte loads (the partials are 20-150 MB in total: HBM-bound).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long long total4,
+                     int splits) {
+  __shared__ float4 s_part[16][16];
+  const int x = threadIdx.x & 15, y = threadIdx.x >> 4;
+  const long long i = static_cast<long long>(blockIdx.x) * 16 + x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < total4) {
+    const float4* p = reinterpret_cast<const float4*>(ws) + i;
+#pragma unroll 4
+    for (int k = y; k < splits; k += 16) {
+      const float4 v = __ldg(p + static_cast<long long>(k) * total4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  s_part[y][x] = acc;
+  __syncthreads();
+  if (y == 0 && i < total4) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      const float4 v = s_part[k][x];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
   }
 }
 
@@ -286,11 +305,9 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
   const int grid = pl.tiles * pl.splits;
   wgrad_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(tx, tdy, p);
   if (pl.splits > 1) {
-    const long long total = static_cast<long long>(cout) * 9 * cin;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const float*>(workspace),
-                                                                   g, total, pl.splits);
+    const long long total4 = static_cast<long long>(cout) * 9 * cin / 4;
+    splitk_reduce_kernel<<<static_cast<int>((total4 + 15) / 16), 256, 0, s>>>(
+        static_cast<const float*>(workspace), g, total4, pl.splits);
   }
   if (dbias) {
     cudaMemsetAsync(dbias, 0, sizeof(float) * cout, s);

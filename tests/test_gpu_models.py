@@ -119,19 +119,34 @@ def test_discriminator_vs_reference_golden(cuda, golden_dir):
     for k, ref in g["grads"].items():
         if g["grad_norms"][k] > 1e-2 * top:
             assert cos(grads[k], ref) > 0.85, k
-    emu = S.discriminator_state(g["seed"], g["shape"], g["features"], g["strides"])
-    names = O.trainable_names(emu)
-    leaf = O._leaf(emu, names)
-    xe = g["x"].clone().requires_grad_(True)
-    with O.emulate_bf16_storage():
-        out_e = O.discriminator_forward(leaf, xe, g["strides"], True)
-        ge = torch.autograd.grad(O.bce(out_e.view(-1), 0.9), [xe] + [leaf[k] for k in names])
+    def emulated(jitter_seed=None):
+        emu = S.discriminator_state(g["seed"], g["shape"], g["features"], g["strides"])
+        names = O.trainable_names(emu)
+        leaf = O._leaf(emu, names)
+        xe = g["x"].clone().requires_grad_(True)
+        with O.emulate_bf16_storage():
+            jit = O.jitter_before_rounding(1e-6, jitter_seed) if jitter_seed is not None else None
+            if jit:
+                jit.__enter__()
+            out_e = O.discriminator_forward(leaf, xe, g["strides"], True)
+            ge = torch.autograd.grad(O.bce(out_e.view(-1), 0.9), [xe] + [leaf[k] for k in names])
+            if jit:
+                jit.__exit__()
+        return names, out_e, ge
+    names, out_e, ge = emulated()
+    _, _, j1 = emulated(1)
+    _, _, j2 = emulated(2)
     assert rel(out, out_e) < 1e-2
-    assert rel(x.grad, ge[0]) < 8e-2
+    # LeakyReLU(0.01) makes every unit that flips branch under bf16 round-off a 100x change, so the
+    # end-to-end gradient is compared against the distance between two jittered oracle runs.
+    # Measured over 6 seeds (tools/gpu_diag_dnoise.py, gpurun_out/t14): CUDA-vs-oracle 0.064-0.101,
+    # oracle-vs-jittered-oracle 0.086-0.116; a single pair of jittered runs scatters by +-30 %, hence
+    # the floor of 0.15 under the 1.5x rule.
+    assert rel(x.grad, ge[0]) < max(0.15, 1.5 * rel(j1[0], j2[0])), rel(j1[0], j2[0])
     top_e = max(float(v.norm()) for v in ge[1:])
-    for k, r in zip(names, ge[1:]):
+    for i, (k, r) in enumerate(zip(names, ge[1:]), 1):
         if float(r.norm()) > 1e-2 * top_e:
-            assert rel(grads[k], r) < 8e-2, k
+            assert rel(grads[k], r) < max(0.15, 1.5 * rel(j1[i], j2[i])), (k, rel(j1[i], j2[i]))
 
 
 @pytest.mark.parametrize("mask", [0b00010, 0b10000, 0b01111])
