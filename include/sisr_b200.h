@@ -40,6 +40,10 @@ typedef struct sisr_conv_desc {
 
 const char* sisr_last_error(void);
 int sisr_abi_version(void);
+/* number of partial-sum rows of a `stats` buffer (= SM count: one row per persistent CTA) */
+int sisr_stats_rows(void);
+/* debug / A-B timing: 1 = always feed the conv engine with im2col-mode TMA (never the tiled-mode boxes) */
+int sisr_debug_force_im2col(int on);
 /* 1 if the tcgen05 implicit-GEMM engine takes this fprop/dgrad shape, 0 if the CUDA-core kernel does */
 int sisr_conv_uses_tensor_cores(const sisr_conv_desc* d);
 
@@ -93,8 +97,9 @@ int sisr_weight_grad_finish(const float* g_prepared, const float* w_orig, const 
 /* ---- convolutions: nn.Conv2d at model_generator.py:10,13,33,39,45,52,123,
  *      model_discriminator.py:10,39 and torchvision vgg19.features (model_content_extractor.py:43) ---- */
 /* y (bf16 NHWC, or pixel-shuffled) and/or y_nchw_f32 (fp32 NCHW, edge layers only) = act(conv(x)+bias).
- * stats (nullable): fp32 [2*cout] overwritten with per-channel {sum, sum of squares} of y (BN batch
- * statistics, fused in the conv epilogue on the tensor-core path). */
+ * stats (nullable): fp32 [sisr_stats_rows()][2*cout], overwritten: row r holds the per-channel {sum, sum of
+ * squares} of y over the output tiles of CTA r (BN batch statistics fused in the conv epilogue, no
+ * atomics); sisr_bn_finalize adds the rows. */
 int sisr_conv_fprop(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16* w_fprop,
                     const float* bias, int act, float slope, const float* slope_ptr, sisr_bf16* y,
                     float* y_nchw_f32, float* stats, void* stream);
@@ -111,7 +116,8 @@ int sisr_conv_wgrad(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
 /* ---- BatchNorm2d (train / eval) fused with PReLU / LeakyReLU / residual add:
  *      model_generator.py:11-14,16-19,40,93 and model_discriminator.py:11-12 ---- */
 int sisr_bn_stats(const sisr_bf16* y, long long rows, int c, float* stats, void* stream);
-int sisr_bn_finalize(const float* stats, float count, const float* gamma, const float* beta,
+/* stats: [stats_rows][2c] partial sums (stats_rows = 1 for sisr_bn_stats output) */
+int sisr_bn_finalize(const float* stats, int stats_rows, float count, const float* gamma, const float* beta,
                      float* running_mean, float* running_var, long long* num_batches_tracked,
                      float momentum, float eps, int training, float* scale, float* shift, float* mean,
                      float* invstd, int c, void* stream);

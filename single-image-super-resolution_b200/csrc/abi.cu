@@ -63,7 +63,9 @@ SimtConv simt_of(const sisr_conv_desc* d) {
 extern "C" {
 
 const char* sisr_last_error(void) { return g_err; }
-int sisr_abi_version(void) { return 1; }
+int sisr_abi_version(void) { return 2; }
+int sisr_stats_rows(void) { return igemm_max_ctas(); }
+int sisr_debug_force_im2col(int on) { igemm_force_im2col(on); return 0; }
 int sisr_conv_uses_tensor_cores(const sisr_conv_desc* d) { return desc_ok(d) && tc_shape(d) ? 1 : 0; }
 
 // ------------------------------------------------------------------ layout
@@ -119,7 +121,6 @@ int sisr_conv_fprop(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
                     float* stats, void* s) {
   if (!desc_ok(d)) return fail(1, "conv_fprop: inconsistent descriptor");
   if (act == SISR_ACT_PRELU && !slope_ptr) return fail(1, "conv_fprop: PReLU needs slope_ptr");
-  if (stats) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * d->cout, S(s));
   if (tc_shape(d) && y && !y_nchw_f32 && act != SISR_ACT_TANH) {
     IgemmProblem p{};
     p.x = B(x); p.NB = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin;
@@ -140,9 +141,12 @@ int sisr_conv_fprop(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
     }
     p.osy = p.osx = 1; p.opy = p.opx = 0;
     p.bias = bias; p.act = act; p.slope = slope; p.slope_ptr = slope_ptr; p.stats = stats;
+    p.stats_rows = igemm_max_ctas();
     if (int rc = igemm_launch(p, S(s))) return fail(rc, "conv_fprop: %s", igemm_last_error());
     return 0;
   }
+  // CUDA-core paths: totals in row 0, the other rows zero
+  if (stats) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * d->cout * igemm_max_ctas(), S(s));
   if (d->ps_r == 2) return fail(1, "conv_fprop: PixelShuffle store needs a tensor-core shape");
   if (thin_geometry(d) && d->cin == 3 && y && !y_nchw_f32 && act != SISR_ACT_TANH) {
     const ThinConv t = thin_of(d, d->cin, d->cout);
@@ -302,11 +306,11 @@ int sisr_bn_stats(const sisr_bf16* y, long long rows, int c, float* stats, void*
   cudaMemsetAsync(stats, 0, sizeof(float) * 2 * c, S(s));
   return wrap(col_stats(B(y), rows, c, stats, 1, S(s)), "bn_stats");
 }
-int sisr_bn_finalize(const float* stats, float count, const float* gamma, const float* beta,
+int sisr_bn_finalize(const float* stats, int stats_rows, float count, const float* gamma, const float* beta,
                      float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                      int training, float* scale, float* shift, float* mean, float* invstd, int c,
                      void* s) {
-  return wrap(bn_finalize(stats, count, gamma, beta, running_mean, running_var, nbt, momentum, eps,
+  return wrap(bn_finalize(stats, stats_rows, count, gamma, beta, running_mean, running_var, nbt, momentum, eps,
                           training, scale, shift, mean, invstd, c, S(s)),
               "bn_finalize");
 }

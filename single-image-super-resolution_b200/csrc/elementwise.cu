@@ -181,7 +181,7 @@ __global__ void col_stats_kernel(const __nv_bfloat16* __restrict__ y, long long 
 }
 
 // ------------------------------------------------------------------ BatchNorm finalize
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int stats_rows, float count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches, float momentum, float eps,
@@ -192,8 +192,14 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
   if (c >= C) return;
   float mean, var;
   if (training) {
-    mean = stats[c] / count;
-    var = fmaxf(stats[C + c] / count - mean * mean, 0.f);
+    float s1 = 0.f, s2 = 0.f;   // add the per-CTA partial rows written by the conv epilogue
+#pragma unroll 4
+    for (int r = 0; r < stats_rows; ++r) {
+      s1 += stats[static_cast<size_t>(r) * 2 * C + c];
+      s2 += stats[static_cast<size_t>(r) * 2 * C + C + c];
+    }
+    mean = s1 / count;
+    var = fmaxf(s2 / count - mean * mean, 0.f);
     const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
@@ -586,11 +592,11 @@ int col_stats(const __nv_bfloat16* y, long long M, int C, float* stats, int with
                                                                                     with_sq);
   return check();
 }
-int bn_finalize(const float* stats, float count, const float* gamma, const float* beta,
+int bn_finalize(const float* stats, int stats_rows, float count, const float* gamma, const float* beta,
                 float* running_mean, float* running_var, long long* num_batches, float momentum,
                 float eps, int training, float* scale, float* shift, float* mean, float* invstd, int C,
                 cudaStream_t s) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, count, gamma, beta, running_mean,
+  bn_finalize_kernel<<<(C + 31) / 32, 32, 0, s>>>(stats, stats_rows, count, gamma, beta, running_mean,
                                                      running_var, num_batches, momentum, eps, training,
                                                      scale, shift, mean, invstd, C);
   return check();

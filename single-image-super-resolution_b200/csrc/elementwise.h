@@ -15,7 +15,7 @@ int tanh_bwd_nchw_to_nhwc(const float* dout, const float* y, __nv_bfloat16* dpre
 int transpose_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, int batch, int R, int Cc, cudaStream_t s);
 
 int col_stats(const __nv_bfloat16* y, long long M, int C, float* stats, int with_sq, cudaStream_t s);
-int bn_finalize(const float* stats, float count, const float* gamma, const float* beta,
+int bn_finalize(const float* stats, int stats_rows, float count, const float* gamma, const float* beta,
                 float* running_mean, float* running_var, long long* num_batches, float momentum,
                 float eps, int training, float* scale, float* shift, float* mean, float* invstd, int C,
                 cudaStream_t s);

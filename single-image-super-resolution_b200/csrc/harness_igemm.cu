@@ -182,7 +182,7 @@ static void fill_fprop_problem(IgemmProblem& p, const ConvCase& cc, const __nv_b
     p.OH = OH; p.OW = OW; p.ldc = cc.Cout; p.ps_c = 0;
   }
   p.osy = p.osx = 1; p.opy = p.opx = 0;
-  p.bias = bias; p.act = cc.act; p.slope = 0.01f; p.slope_ptr = slope; p.stats = stats;
+  p.bias = bias; p.act = cc.act; p.slope = 0.01f; p.slope_ptr = slope; p.stats = stats; p.stats_rows = igemm_max_ctas();
 }
 
 static int run_conv(const ConvCase& cc, bool timing) {
@@ -198,14 +198,15 @@ static int run_conv(const ConvCase& cc, bool timing) {
   float *dbias, *dslope, *dstats;
   CK(cudaMalloc(&dx, nx * 2)); CK(cudaMalloc(&dw, nw * 2)); CK(cudaMalloc(&dy, ny * 2));
   CK(cudaMalloc(&dref, ny * 2)); CK(cudaMalloc(&dbias, cc.Cout * 4)); CK(cudaMalloc(&dslope, 4));
-  CK(cudaMalloc(&dstats, 2 * cc.Cout * 4));
+  const int srows = igemm_max_ctas();
+  CK(cudaMalloc(&dstats, (size_t)srows * 2 * cc.Cout * 4));
   CK(cudaMemcpy(dx, hx.data(), nx * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw, hw.data(), nw * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dbias, hb.data(), cc.Cout * 4, cudaMemcpyHostToDevice));
   const float slope = 0.25f;
   CK(cudaMemcpy(dslope, &slope, 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dy, 0xFF, ny * 2));
-  CK(cudaMemset(dstats, 0, 2 * cc.Cout * 4));
+  CK(cudaMemset(dstats, 0xFF, (size_t)srows * 2 * cc.Cout * 4));   // the kernel must overwrite every row
 
   IgemmProblem p;
   fill_fprop_problem(p, cc, dx, dw, dy, dbias, dslope, cc.stats ? dstats : nullptr);
@@ -256,8 +257,11 @@ static int run_conv(const ConvCase& cc, bool timing) {
   printf("[conv %s] rel_l2=%.3e max_abs=%.3e bad=%zu -> %s\n", cc.name, rel, maxabs, nbad,
          fail ? "FAIL" : "ok");
   if (cc.stats) {
-    std::vector<float> hs(2 * cc.Cout);
-    CK(cudaMemcpy(hs.data(), dstats, 2 * cc.Cout * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> hr((size_t)srows * 2 * cc.Cout);
+    CK(cudaMemcpy(hr.data(), dstats, hr.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<double> hs(2 * cc.Cout, 0.0);
+    for (int r = 0; r < srows; ++r)
+      for (int c = 0; c < 2 * cc.Cout; ++c) hs[c] += hr[(size_t)r * 2 * cc.Cout + c];
     double worst = 0;
     for (int c = 0; c < cc.Cout; ++c) {
       worst = fmax(worst, fabs(hs[c] - ssum[c]) / (fabs(ssum[c]) + 1.0));

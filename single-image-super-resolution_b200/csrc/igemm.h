@@ -47,12 +47,16 @@ struct IgemmProblem {
   int act;                 // Act
   float slope;             // ACT_LEAKY
   const float* slope_ptr;  // ACT_PRELU (single learnable slope)
-  float* stats;            // [2*Cout] += {sum, sum of squares} of the stored bf16 values, or nullptr
+  float* stats;            // [stats_rows][2*Cout]: row r = {sum, sum of squares} of the stored bf16 values
+                           // over the tiles of CTA r (rows >= grid are zeroed), or nullptr
+  int stats_rows;          // >= igemm_max_ctas()
 };
 
 // Returns 0 on success; message via igemm_last_error().
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream);
 bool igemm_supported(const IgemmProblem& p);
+void igemm_force_im2col(int on);   // 1: never use the tiled-mode A loads (debug / A-B timing)
+int igemm_max_ctas();   // the persistent grid never exceeds this (number of SMs)
 const char* igemm_last_error();
 
 }  // namespace sisr

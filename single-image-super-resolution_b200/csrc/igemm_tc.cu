@@ -30,6 +30,10 @@ constexpr int kMaxCout = 512;   // per-CTA BN statistics accumulator
 struct KParams {
   int M, GH, GW, trav_stride, lower_w, lower_h;
   int cin_blocks, num_taps, n_tiles, m_tiles;
+  // tiled A loads (stride-1 same-size convs): an M tile is a TH x TW pixel rectangle of one image,
+  // fetched per tap as ONE tiled-mode TMA box {64 ch, TW, TH} shifted by the tap offset (zero fill
+  // outside the image = conv padding); tiled = 0: im2col-mode TMA over 128 consecutive positions
+  int tiled, TW, TH, tiles_w, tiles_hw, a_bytes;
   IgemmTaps taps;
   __nv_bfloat16* out;
   int OH, OW, ldc, osy, osx, opy, opx, ps_c;
@@ -38,6 +42,7 @@ struct KParams {
   float slope;
   const float* slope_ptr;
   float* stats;
+  int stats_rows;
 };
 
 template <int BN>
@@ -120,12 +125,21 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int hw = p.GH * p.GW;
       uint32_t kbg = 0;   // k-block counter across tiles (pipeline stage / phase)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * kBM;
+        const int tile_m = tile / p.n_tiles;
         const int n0 = (tile % p.n_tiles) * BN;
-        const int n_img = m0 / hw;
-        const int rem = m0 - n_img * hw;
-        const int gh = rem / p.GW;
-        const int gw = rem - gh * p.GW;
+        int n_img, gh, gw;
+        if (p.tiled) {
+          n_img = tile_m / p.tiles_hw;
+          const int r2 = tile_m - n_img * p.tiles_hw;
+          gh = (r2 / p.tiles_w) * p.TH;
+          gw = (r2 % p.tiles_w) * p.TW;
+        } else {
+          const int m0 = tile_m * kBM;
+          n_img = m0 / hw;
+          const int rem = m0 - n_img * hw;
+          gh = rem / p.GW;
+          gw = rem - gh * p.GW;
+        }
         const int cw = gw * p.trav_stride + p.lower_w;
         const int ch = gh * p.trav_stride + p.lower_h;
         for (int tap = 0; tap < p.num_taps; ++tap) {
@@ -134,11 +148,15 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t round = kbg / STAGES;
             mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);
             const uint32_t fb = smem_u32(&full_bar[s]);
-            mbar_expect_tx(fb, L::kStageBytes);
+            mbar_expect_tx(fb, p.a_bytes + L::kBTileBytes);
             const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
             const uint32_t b_dst = a_dst + kATileBytes;
-            tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * kBK, cw, ch, n_img, p.taps.off_w[tap],
-                               p.taps.off_h[tap]);
+            if (p.tiled)
+              tma_load_4d(a_dst, &tmap_a, fb, cb * kBK, cw + p.taps.off_w[tap], ch + p.taps.off_h[tap],
+                          n_img);
+            else
+              tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * kBK, cw, ch, n_img, p.taps.off_w[tap],
+                                 p.taps.off_h[tap]);
             tma_load_2d(b_dst, &tmap_b, fb, p.taps.k_off[tap] + cb * kBK, n0);
           }
         }
@@ -183,15 +201,28 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, use = it >> 1;
-      const int m0 = (tile / p.n_tiles) * kBM;
+      const int tile_m = tile / p.n_tiles;
       const int n0 = (tile % p.n_tiles) * BN;
-      const int row = m0 + quad * 32 + lane;
-      const bool valid = row < p.M;
-      const int rr = valid ? row : 0;
-      const int n_img = rr / hw;
-      const int rem = rr - n_img * hw;
-      const int gh = rem / p.GW;
-      const int gw = rem - gh * p.GW;
+      int n_img, gh, gw;
+      bool valid;
+      if (p.tiled) {
+        const int r = quad * 32 + lane;
+        n_img = tile_m / p.tiles_hw;
+        const int r2 = tile_m - n_img * p.tiles_hw;
+        const int th = r / p.TW;
+        gh = (r2 / p.tiles_w) * p.TH + th;
+        gw = (r2 % p.tiles_w) * p.TW + (r - th * p.TW);
+        valid = th < p.TH && gh < p.GH && gw < p.GW;
+        if (!valid) gh = gw = 0;
+      } else {
+        const int row = tile_m * kBM + quad * 32 + lane;
+        valid = row < p.M;
+        const int rr = valid ? row : 0;
+        n_img = rr / hw;
+        const int rem = rr - n_img * hw;
+        gh = rem / p.GW;
+        gw = rem - gh * p.GW;
+      }
 
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
       tc_fence_after();
@@ -257,10 +288,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
     }
     if (p.stats) {
+      // per-CTA partial sums, plain stores (no contended atomics); bn_finalize adds the rows
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) {
-        const float sv = s_stats[i];
-        if (sv != 0.f) atomicAdd(&p.stats[i], sv);
+      float* mine = p.stats + static_cast<size_t>(blockIdx.x) * 2 * cout;
+      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) mine[i] = s_stats[i];
+      for (int r = gridDim.x + blockIdx.x; r < p.stats_rows; r += gridDim.x) {
+        float* z = p.stats + static_cast<size_t>(r) * 2 * cout;
+        for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) z[i] = 0.f;
       }
     }
   }
@@ -296,6 +330,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
   return 0;
 }
 
+bool g_force_im2col = false;   // igemm_force_im2col(): A/B switch for benchmarks and tests
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -332,9 +367,12 @@ int pick_bn(int m_tiles, int cout, int ps_c, int num_kb) {
 }  // namespace
 
 const char* igemm_last_error() { return g_err; }
+int igemm_max_ctas() { return num_sms(); }
+void igemm_force_im2col(int on) { g_force_im2col = on != 0; }
 
 bool igemm_supported(const IgemmProblem& p) {
   if (p.Cin % 64 || p.Cout % 64 || p.Cout > kMaxCout) return false;
+  if (p.stats && p.stats_rows < num_sms()) return false;
   if (p.num_taps < 1 || p.num_taps > kMaxTaps) return false;
   if (p.ldc % 8) return false;
   if (p.ps_c > 0 && (p.ps_c % 32)) return false;
@@ -351,15 +389,34 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     return 1;
   }
   const long long M = static_cast<long long>(p.NB) * p.GH * p.GW;
-  const int m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  int m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  // rectangular M tiles + tiled-mode TMA when a rectangle covers the image with >= 85 % useful rows
+  int tw = 0, th = 0, tiles_w = 0, tiles_h = 0;
+  if (p.trav_stride == 1 && p.GH == p.H && p.GW == p.W && !g_force_im2col) {
+    const int cand_w[7] = {p.W <= 128 ? p.W : 0, 128, 64, 32, 16, 8, 4};
+    double best = 0.0;
+    for (int i = 0; i < 7; ++i) {
+      const int cw = cand_w[i];
+      if (cw <= 0 || cw > p.W) continue;
+      const int chh = 128 / cw;
+      const int nw = (p.W + cw - 1) / cw, nh = (p.H + chh - 1) / chh;
+      const double eff = static_cast<double>(p.H) * p.W / (static_cast<double>(nw) * nh * 128.0);
+      if (eff > best + 1e-9) {
+        best = eff; tw = cw; th = chh; tiles_w = nw; tiles_h = nh;
+      }
+    }
+    if (best < 0.85) tw = 0;
+  }
+  if (tw) m_tiles = p.NB * tiles_h * tiles_w;
   const int bn = pick_bn(m_tiles, p.Cout, p.ps_c, p.num_taps * (p.Cin / kBK));
   if (!bn) {
     snprintf(g_err, sizeof g_err, "igemm: no tile for Cout=%d", p.Cout);
     return 1;
   }
   CUtensorMap ta, tb;
-  if (make_tmap_im2col_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, p.lower_w, p.lower_h, p.upper_w,
-                                 p.upper_h, kBK, kBM, p.trav_stride)) {
+  if (tw ? make_tmap_tiled_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, kBK, tw, th)
+         : make_tmap_im2col_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, p.lower_w, p.lower_h, p.upper_w,
+                                      p.upper_h, kBK, kBM, p.trav_stride)) {
     snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
     return 2;
   }
@@ -378,6 +435,9 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.num_taps = p.num_taps;
   kp.n_tiles = p.Cout / bn;
   kp.m_tiles = m_tiles;
+  kp.tiled = tw ? 1 : 0;
+  kp.TW = tw; kp.TH = th; kp.tiles_w = tiles_w; kp.tiles_hw = tiles_w * tiles_h;
+  kp.a_bytes = tw ? tw * th * kBK * 2 : kATileBytes;
   kp.taps = p.taps;
   kp.out = p.out;
   kp.OH = p.OH;
@@ -393,6 +453,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.slope = p.slope;
   kp.slope_ptr = p.slope_ptr;
   kp.stats = p.stats;
+  kp.stats_rows = p.stats_rows;
   const int tiles = m_tiles * kp.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   switch (bn) {

@@ -54,6 +54,29 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+int make_tmap_tiled_nhwc_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C,
+                              uint32_t channels, uint32_t box_w, uint32_t box_h) {
+  std::call_once(g_once, load_entry_points);
+  if (!g_encode_tiled) {
+    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point unavailable");
+    return 1;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * W * 2, (cuuint64_t)C * W * H * 2};
+  cuuint32_t box[4] = {channels, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled(4d) failed (%d): NHWC=%d,%d,%d,%d box=%u,%u,%u",
+             (int)r, N, H, W, C, channels, box_w, box_h);
+    return 2;
+  }
+  return 0;
+}
+
 int make_tmap_im2col_nhwc_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C,
                                int lower_w, int lower_h, int upper_w, int upper_h,
                                uint32_t channels, uint32_t pixels, uint32_t trav_stride) {

@@ -22,6 +22,11 @@ int make_tmap_im2col_nhwc_bf16(CUtensorMap* out, const void* base, int N, int H,
                                int lower_w, int lower_h, int upper_w, int upper_h,
                                uint32_t channels, uint32_t pixels, uint32_t trav_stride);
 
+// tiled-mode descriptor over an NHWC bf16 tensor [N, H, W, C]: box = {channels, box_w, box_h, 1},
+// 128-byte swizzle, zero fill outside the tensor (negative / overflowing coordinates allowed).
+int make_tmap_tiled_nhwc_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C,
+                              uint32_t channels, uint32_t box_w, uint32_t box_h);
+
 const char* tmap_last_error();
 
 }  // namespace sisr

@@ -45,6 +45,16 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_stats_rows = [0]
+
+
+def stats_rows() -> int:
+    """Rows of a conv ``stats`` buffer: one partial-sum row per persistent CTA (SM count)."""
+    if not _stats_rows[0]:
+        _stats_rows[0] = int(query("sisr_stats_rows"))
+    return _stats_rows[0]
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise _lib.SisrError(f"{what}: tensor is on {t.device}; the sisr_b200 operators run only on "
@@ -260,7 +270,7 @@ class Conv2dFn(torch.autograd.Function):
                 bias_used = torch.empty_like(bias)
             call("sisr_weight_prep", weight, sigma, bias, wf, wd, bias_used if cfg.ps_r == 2 else None,
                  cout, cin, k, cfg.ps_r, st)
-        stats = torch.empty(2 * cout, dtype=torch.float32, device=dev) if cfg.want_stats else None
+        stats = torch.empty((stats_rows(), 2 * cout), dtype=torch.float32, device=dev) if cfg.want_stats else None
         if cfg.out_nchw_f32:
             y = torch.empty((d.n, cout, d.oh, d.ow), dtype=torch.float32, device=dev)
             call("sisr_conv_fprop", d, x, wf, bias_used, cfg.act, cfg.leaky_slope, slope, None, y, None, st)
@@ -361,17 +371,17 @@ class BnActFn(torch.autograd.Function):
         count = float(rows)
         if cfg.training:
             if stats is None:
-                stats = torch.empty(2 * c, dtype=torch.float32, device=dev)
+                stats = torch.empty((1, 2 * c), dtype=torch.float32, device=dev)
                 call("sisr_bn_stats", y, rows, c, stats, st)
             world = _world() if cfg.sync else 1
             if world > 1:
-                stats = stats.clone()
+                stats = stats.sum(dim=0, keepdim=True) if stats.shape[0] > 1 else stats.clone()
                 _all_reduce(stats)
                 count *= world
         else:
-            stats = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+            stats = torch.zeros((1, 2 * c), dtype=torch.float32, device=dev)
         aux = torch.empty((4, c), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
-        call("sisr_bn_finalize", stats, count, gamma, beta, running_mean, running_var, nbt,
+        call("sisr_bn_finalize", stats, stats.shape[0], count, gamma, beta, running_mean, running_var, nbt,
              cfg.momentum, cfg.eps, 1 if cfg.training else 0, aux[0], aux[1], aux[2], aux[3], c, st)
         out = torch.empty_like(y)
         if residual is not None:

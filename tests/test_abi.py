@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in protos:
         assert hasattr(lib, name), f"{name} declared in include/sisr_b200.h but not exported"
     lib.sisr_abi_version.restype = ctypes.c_int
-    assert lib.sisr_abi_version() == 1
+    assert lib.sisr_abi_version() == 2
 
 
 def test_tensor_core_shape_predicate(built):

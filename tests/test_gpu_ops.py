@@ -90,6 +90,8 @@ def test_conv_forward_backward(cuda, case):
     y, stats = ops.Conv2dFn.apply(xd, wd, bd, None, None, sd, cfg)
     assert rel(nchw(y), y_ref) < TOL_BF16
     if stats is not None:
+        assert stats.shape == (ops.stats_rows(), 2 * cout)      # one partial-sum row per persistent CTA
+        stats = stats.double().sum(dim=0)
         yy = nchw(y).double()
         assert rel(stats[:cout], yy.sum(dim=(0, 2, 3))) < 1e-3 or float(yy.sum().abs()) < 1
         assert rel(stats[cout:], (yy * yy).sum(dim=(0, 2, 3))) < 1e-3
