@@ -199,7 +199,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     batch = args.batch
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph      # NCCL all-reduces and the peer-memory SyncBN kernels are captured too
     gs = parallel.GradSync() if world > 1 else None
     tr = build_trainer(dev, batch, world, gs)
     hr_host = S.synthetic_hr(1234 + rank, batch, 96).pin_memory()

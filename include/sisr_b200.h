@@ -162,6 +162,29 @@ int sisr_mse_fwd(const float* a, const float* b, long long n, float coef, float*
 int sisr_mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
                  float* gb, void* stream);
 
+/* ---- data parallelism: replaces nn.DataParallel (config.py:114-118).  Gradient all-reduce is NCCL (host
+ *      side, parallel.py); the per-layer SyncBN statistic exchange runs over NVLink peer memory:
+ *      every rank allocates one workspace (sisr_peer_alloc), publishes its CUDA-IPC handle, maps the
+ *      peers' workspaces (sisr_peer_open) and passes the HOST array bases[world] (own pointer at
+ *      bases[rank]) to the calls below.  slot: a distinct index in [0, 512) per exchange of a step,
+ *      the same on every rank.  Results are bit-identical on all ranks. ---- */
+size_t sisr_peer_workspace_bytes(void);
+int sisr_peer_handle_bytes(void);
+int sisr_peer_alloc(void** ptr);
+int sisr_peer_free(void* ptr);
+int sisr_peer_get_handle(void* ptr, void* handle);
+int sisr_peer_open(const void* handle, void** ptr);
+int sisr_peer_close(void* ptr);
+/* buf[i] <- sum over ranks of buf[i], i < n <= 1152 */
+int sisr_peer_allreduce(void* const* bases, int rank, int world, int slot, float* buf, int n, void* stream);
+/* sisr_bn_finalize (training) on the global batch: local partial rows are added, the [2c] sums are
+ * exchanged, count = global number of elements per channel */
+int sisr_bn_finalize_sync(void* const* bases, int rank, int world, int slot, const float* stats,
+                          int stats_rows, float count, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches_tracked,
+                          float momentum, float eps, float* scale, float* shift, float* mean,
+                          float* invstd, int c, void* stream);
+
 /* ---- optimiser: torch.optim.Adam + LambdaLR (config.py:170-180, 293-294; train.py:75,108,121-122) ---- */
 int sisr_adam_tick(int* step, float lr0, float decay, float b1, float b2, float* hyper, void* stream);
 /* p/g/m/v/numel are HOST arrays of n device pointers / element counts */

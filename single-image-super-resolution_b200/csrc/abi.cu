@@ -4,6 +4,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "conv_simt.h"
 #include "conv_thin.h"
@@ -11,6 +12,7 @@
 #include "igemm.h"
 #include "linear.h"
 #include "optim.h"
+#include "peer.h"
 #include "spectral.h"
 #include "wgrad_tc.h"
 
@@ -377,6 +379,57 @@ int sisr_mse_fwd(const float* a, const float* b, long long n, float coef, float*
 int sisr_mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
                  float* gb, void* s) {
   return wrap(mse_bwd(a, b, n, coef, gout, ga, gb, S(s)), "mse_bwd");
+}
+
+// ------------------------------------------------------------------ SyncBN over NVLink peer memory
+size_t sisr_peer_workspace_bytes(void) { return peer_workspace_bytes(); }
+int sisr_peer_handle_bytes(void) { return static_cast<int>(sizeof(cudaIpcMemHandle_t)); }
+int sisr_peer_alloc(void** ptr) {
+  if (!ptr) return fail(1, "peer_alloc: null argument");
+  cudaError_t e = cudaMalloc(ptr, peer_workspace_bytes());
+  if (e == cudaSuccess) e = cudaMemset(*ptr, 0, peer_workspace_bytes());
+  if (e != cudaSuccess) return fail(2, "peer_alloc: %s", cudaGetErrorString(e));
+  return 0;
+}
+int sisr_peer_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? 0 : fail(2, "peer_free failed"); }
+int sisr_peer_get_handle(void* ptr, void* handle) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) return fail(2, "peer_get_handle: %s", cudaGetErrorString(e));
+  memcpy(handle, &h, sizeof h);
+  return 0;
+}
+int sisr_peer_open(const void* handle, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(2, "peer_open: %s", cudaGetErrorString(e));
+  return 0;
+}
+int sisr_peer_close(void* ptr) {
+  return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? 0 : fail(2, "peer_close failed");
+}
+static PeerTable make_table(void* const* bases, int rank, int world) {
+  PeerTable t{};
+  t.rank = rank;
+  t.world = world;
+  for (int r = 0; r < world && r < kPeerMaxWorld; ++r) t.base[r] = bases[r];
+  return t;
+}
+int sisr_peer_allreduce(void* const* bases, int rank, int world, int slot, float* buf, int n, void* s) {
+  if (!bases || world > kPeerMaxWorld) return fail(1, "peer_allreduce: bad arguments");
+  return wrap(peer_allreduce(make_table(bases, rank, world), slot, buf, n, S(s)), "peer_allreduce");
+}
+int sisr_bn_finalize_sync(void* const* bases, int rank, int world, int slot, const float* stats,
+                          int stats_rows, float count, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* nbt, float momentum,
+                          float eps, float* scale, float* shift, float* mean, float* invstd, int c,
+                          void* s) {
+  if (!bases || world > kPeerMaxWorld) return fail(1, "bn_finalize_sync: bad arguments");
+  return wrap(bn_finalize_sync(make_table(bases, rank, world), slot, stats, stats_rows, count, gamma,
+                               beta, running_mean, running_var, nbt, momentum, eps, scale, shift, mean,
+                               invstd, c, S(s)),
+              "bn_finalize_sync");
 }
 
 // ------------------------------------------------------------------ optimiser

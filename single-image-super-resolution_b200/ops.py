@@ -70,6 +70,22 @@ def set_sync_group(group):
     _dist_group = group
 
 
+_peer = None
+
+
+def set_peer_exchange(px):
+    """parallel.PeerExchange used for SyncBN (None: all-reduce through the process group)."""
+    global _peer
+    _peer = px
+
+
+def begin_step():
+    """Called by the trainer at the start of every step (all ranks): resets per-step numbering."""
+    _colsum_cache.clear()
+    if _peer is not None:
+        _peer.reset()
+
+
 def _world():
     import torch.distributed as dist
     if _dist_group is None or not dist.is_initialized():
@@ -375,14 +391,21 @@ class BnActFn(torch.autograd.Function):
                 call("sisr_bn_stats", y, rows, c, stats, st)
             world = _world() if cfg.sync else 1
             if world > 1:
-                stats = stats.sum(dim=0, keepdim=True) if stats.shape[0] > 1 else stats.clone()
-                _all_reduce(stats)
                 count *= world
+                if _peer is None:
+                    stats = stats.sum(dim=0, keepdim=True) if stats.shape[0] > 1 else stats.clone()
+                    _all_reduce(stats)
         else:
             stats = torch.zeros((1, 2 * c), dtype=torch.float32, device=dev)
         aux = torch.empty((4, c), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
-        call("sisr_bn_finalize", stats, stats.shape[0], count, gamma, beta, running_mean, running_var, nbt,
-             cfg.momentum, cfg.eps, 1 if cfg.training else 0, aux[0], aux[1], aux[2], aux[3], c, st)
+        if cfg.training and cfg.sync and _world() > 1 and _peer is not None:
+            # global-batch statistics: partial rows + NVLink peer exchange + finalize in one kernel
+            call("sisr_bn_finalize_sync", _peer.bases, _peer.rank, _peer.world, _peer.next_slot(), stats,
+                 stats.shape[0], count, gamma, beta, running_mean, running_var, nbt, cfg.momentum,
+                 cfg.eps, aux[0], aux[1], aux[2], aux[3], c, st)
+        else:
+            call("sisr_bn_finalize", stats, stats.shape[0], count, gamma, beta, running_mean, running_var, nbt,
+                 cfg.momentum, cfg.eps, 1 if cfg.training else 0, aux[0], aux[1], aux[2], aux[3], c, st)
         out = torch.empty_like(y)
         if residual is not None:
             residual = residual.contiguous()
@@ -411,7 +434,11 @@ class BnActFn(torch.autograd.Function):
         if cfg.training:
             if cfg.sync and _world() > 1:
                 sums = sums.clone()
-                _all_reduce(sums)
+                if _peer is not None:
+                    call("sisr_peer_allreduce", _peer.bases, _peer.rank, _peer.world, _peer.next_slot(),
+                         sums, 2 * c + 1, st)
+                else:
+                    _all_reduce(sums)
             red = sums
         else:
             red = torch.zeros_like(sums)   # eval mode: statistics are constants

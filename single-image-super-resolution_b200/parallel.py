@@ -32,7 +32,51 @@ def init_distributed(backend: str = "nccl"):
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     if world > 1:
         ops.set_sync_group(dist.group.WORLD)
+        if backend == "nccl":
+            ops.set_peer_exchange(PeerExchange(dist.group.WORLD))
     return rank, local, world
+
+
+class PeerExchange:
+    """NVLink peer-memory workspace for the per-layer SyncBN statistic exchange (one small kernel
+    per exchange, see csrc/peer.cu).  Every rank cudaMallocs one workspace, the CUDA-IPC handles are
+    all-gathered once, and each rank maps the workspaces of its peers."""
+
+    SLOTS = 512
+
+    def __init__(self, group=None):
+        import ctypes
+        from ._lib import call
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise RuntimeError("PeerExchange supports up to 8 ranks (one NVLink domain)")
+        own = ctypes.c_void_p()
+        call("sisr_peer_alloc", ctypes.byref(own))
+        handle = ctypes.create_string_buffer(64)
+        call("sisr_peer_get_handle", own, handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.bases = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                self.bases[r] = own.value
+            else:
+                mapped = ctypes.c_void_p()
+                call("sisr_peer_open", handles[r], ctypes.byref(mapped))
+                self.bases[r] = mapped.value
+        self._own = own
+        self.slot = 0
+        dist.barrier(group=group)
+
+    def next_slot(self) -> int:
+        s = self.slot
+        self.slot = (s + 1) % self.SLOTS
+        return s
+
+    def reset(self):
+        """Start of a training step: every rank numbers its exchanges from 0 again."""
+        self.slot = 0
 
 
 def broadcast_module(module: torch.nn.Module, src: int = 0):

@@ -1,0 +1,94 @@
+"""Multi-GPU parity check (run with torchrun, one rank per GPU):
+  1. the NVLink peer-memory all-reduce equals the sum of the ranks' vectors, bit-identical on all ranks;
+  2. one data-parallel SRGAN step (batch sharded, SyncBN over peer memory, bucketed NCCL gradient
+     all-reduce) gives the same losses and post-step weights as ONE process on the whole batch.
+usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P tools/multi_gpu_check.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+import sisr_b200 as m
+from sisr_b200 import ops, parallel
+from oracle import state_factory as S
+import torch.nn.functional as F
+
+
+def build(dev, grad_sync, seed=800, shape=(3, 32, 32), feats=(64, 64, 128, 128), strides=(1, 2, 1, 2), mask=0b00010):
+    g_st = S.generator_state(seed, n_blocks=2, n_suffix=1)
+    d_st = S.discriminator_state(seed + 1, shape, list(feats), list(strides))
+    v_st = S.vgg_state(seed + 2, mask)
+    net_g = m.GeneratorSuffix(m.Generator(2, 64, 256, [2], use_sn=True))
+    net_d = m.Discriminator(shape, list(feats), list(strides))
+    ext = m.MaskedVGG(mask)
+    for net, st in ((net_g, g_st), (net_d, d_st), (ext, v_st)):
+        torch.nn.Module.load_state_dict(net, S.clone_state(st), strict=True)
+    net_g, net_d, ext = net_g.to(dev), net_d.to(dev), ext.to(dev)
+    tr = m.SRGANTrainer(net_g, net_d, ext, m.StepConfig(lr=1e-3, use_replay=False), grad_sync=grad_sync)
+    if grad_sync is not None:
+        grad_sync.attach(tr.opt_d)
+        grad_sync.attach(tr.opt_g)
+    return tr
+
+
+def main():
+    rank, local, world = parallel.init_distributed()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    ok = True
+    # 1. peer all-reduce
+    px = ops._peer
+    assert px is not None and world > 1
+    for n in (1, 129, 1025):
+        v = torch.arange(n, device=dev, dtype=torch.float32) * (rank + 1) + 0.25 * rank
+        px.reset()
+        for _ in range(3):          # same slot reused across "steps": epochs must advance
+            w = v.clone()
+            ops.call("sisr_peer_allreduce", px.bases, px.rank, px.world, 7, w, n, ops._stream())
+            torch.cuda.synchronize()
+            dist.barrier()
+        want = sum(torch.arange(n, dtype=torch.float32) * (r + 1) + 0.25 * r for r in range(world))
+        good = torch.equal(w.cpu(), want)
+        ok &= good
+        if rank == 0:
+            print(f"peer_allreduce n={n}: {'ok' if good else 'MISMATCH'}", flush=True)
+    # 2. data-parallel step vs single process on the global batch
+    per = 4
+    hr_all = S.synthetic_hr(4321, per * world, 32)
+    lr_all = F.interpolate(hr_all, (8, 8), mode="bicubic", align_corners=True).clamp(-1, 1)
+    tr = build(dev, parallel.GradSync(bucket_bytes=1 << 20))
+    sl = slice(rank * per, (rank + 1) * per)
+    outs = [tr.step(hr_all[sl].to(dev), lr_all[sl].to(dev)) for _ in range(2)]
+    torch.cuda.synchronize()
+    losses = torch.stack([torch.stack([o["err_d"].reshape(()), o["err_g_adv"].reshape(()), o["err_g_cont"].reshape(())])
+                          for o in outs])
+    # the D / G adversarial losses are per-rank means over the local shard: average them
+    dist.all_reduce(losses)
+    losses /= world
+    if rank == 0:
+        ops.set_sync_group(None)
+        ops.set_peer_exchange(None)
+        ref = build(dev, None)
+        routs = [ref.step(hr_all.to(dev), lr_all.to(dev)) for _ in range(2)]
+        rl = torch.stack([torch.stack([o["err_d"].reshape(()), o["err_g_adv"].reshape(()), o["err_g_cont"].reshape(())])
+                          for o in routs])
+        rel = ((losses - rl).abs() / rl.abs()).max().item()
+        print("losses dp:", losses.tolist(), "\nlosses 1p:", rl.tolist(), f"\nmax rel diff {rel:.3e}", flush=True)
+        ok &= rel < 2e-2
+        worst = 0.0
+        for (k, a), (_, b) in zip(tr.net_g.state_dict().items(), ref.net_g.state_dict().items()):
+            if a.dtype.is_floating_point and "running" in k:
+                worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-6)))
+        print(f"BN running statistics (G) worst rel diff vs single process: {worst:.3e}", flush=True)
+        ok &= worst < 2e-2
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if flag.item() == 1.0 else "FAIL", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
