@@ -200,7 +200,10 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     batch = args.batch
     use_graph = not args.no_graph      # NCCL all-reduces and the peer-memory SyncBN kernels are captured too
-    gs = parallel.GradSync() if world > 1 else None
+    gs = parallel.GradSync() if (world > 1 and not os.environ.get("SISR_DIAG_NO_GRADSYNC")) else None
+    if os.environ.get("SISR_DIAG_NO_SYNCBN"):      # attribution experiments only (results differ from the spec)
+        from sisr_b200 import ops as _ops
+        _ops.set_sync_group(None)
     tr = build_trainer(dev, batch, world, gs)
     hr_host = S.synthetic_hr(1234 + rank, batch, 96).pin_memory()
     import torch.nn.functional as F
@@ -246,7 +249,11 @@ def run_ours(args):
     if not use_graph and hasattr(_lib, "LAUNCHES"):
         launches_per_step = (_lib.LAUNCHES[0] - c0) // args.steps
     t = torch.tensor([ms], device=dev)
+    ms_by_rank = [ms / args.steps]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        ms_by_rank = [float(x) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
     # ---- timed region 2: end to end from pinned host buffers
@@ -281,7 +288,8 @@ def run_ours(args):
     line = {
         "metric": "SRGAN x4 train-step HR patches/sec", "value": value, "unit": "patches/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": ms / args.steps, "ms_per_step_by_rank": ms_by_rank,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "SRGAN x4 full training step (G 16 blocks + suffix, D @3x96x96, "
                                "MaskedVGG54 content loss + adversarial loss), 96x96 HR patches",

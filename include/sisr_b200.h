@@ -113,6 +113,19 @@ size_t sisr_conv_wgrad_workspace_bytes(const sisr_conv_desc* d);
 int sisr_conv_wgrad(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16* dy, float* g_prepared,
                     float* dbias_perm, void* workspace, void* stream);
 
+/* sisr_conv_wgrad + sisr_weight_grad_finish in one call (what the autograd operators use): the split-K
+ * partials are reduced, divided by sigma, corrected for the gradient through sigma and re-laid out as
+ * dw [cout,cin,k,k] by one cooperative kernel.  dbias_in (nullable): bias gradient in prepared row order
+ * already reduced by the caller (sisr_bn_bwd_apply / sisr_act_bwd colsum); NULL: computed here.
+ * workspace: sisr_conv_wgrad_fused_workspace_bytes(d) bytes. */
+size_t sisr_conv_wgrad_fused_workspace_bytes(const sisr_conv_desc* d);
+int sisr_conv_wgrad_fused(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16* dy,
+                          const float* w_orig, const float* u, const float* v, const float* sigma,
+                          float* dw, const float* dbias_in, float* dbias, int accumulate, void* workspace,
+                          void* stream);
+/* debug: 1 = never use the cooperative launch (two ordinary kernels instead) */
+int sisr_debug_disable_cooperative(int off);
+
 /* ---- BatchNorm2d (train / eval) fused with PReLU / LeakyReLU / residual add:
  *      model_generator.py:11-14,16-19,40,93 and model_discriminator.py:11-12 ---- */
 int sisr_bn_stats(const sisr_bf16* y, long long rows, int c, float* stats, void* stream);

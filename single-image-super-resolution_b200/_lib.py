@@ -83,7 +83,7 @@ def _conv(a):
 
 # kernels launched per ABI call (for bench.py's ``gpu_launches`` claim); default 1
 _KERNELS_PER_CALL = {"sisr_sn_power_iteration": 3, "sisr_weight_grad_finish": 2, "sisr_dhead_forward": 2,
-                     "sisr_dhead_backward": 3, "sisr_adam_multi": 2, "sisr_conv_wgrad": 3}
+                     "sisr_dhead_backward": 3, "sisr_adam_multi": 2, "sisr_conv_wgrad": 3, "sisr_conv_wgrad_fused": 2}
 LAUNCHES = [0]
 
 

@@ -303,6 +303,51 @@ int sisr_conv_wgrad(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
               "conv_wgrad_simt");
 }
 
+// conv_wgrad + weight_grad_finish in one call: the split-K partials go straight into the fused
+// reduce / spectral-norm / layout kernel (2 launches per layer instead of 5).
+size_t sisr_conv_wgrad_fused_workspace_bytes(const sisr_conv_desc* d) {
+  if (!desc_ok(d)) return 0;
+  const size_t full = sizeof(float) * static_cast<size_t>(d->cout) * d->k * d->k * d->cin;
+  size_t part = wgrad_tc_workspace_bytes(d->n, d->h, d->w, d->cin, d->oh, d->ow, d->cout, d->k, d->stride,
+                                         d->pad, d->ps_r);
+  if (part < full) part = full;
+  return part + sizeof(float) * (static_cast<size_t>(d->cout) + 8);
+}
+int sisr_conv_wgrad_fused(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16* dy,
+                          const float* w_orig, const float* u, const float* v, const float* sigma,
+                          float* dw, const float* dbias_in, float* dbias, int accumulate, void* workspace,
+                          void* s) {
+  if (!desc_ok(d)) return fail(1, "conv_wgrad_fused: inconsistent descriptor");
+  if (!workspace || !dw) return fail(1, "conv_wgrad_fused: null argument");
+  const size_t full = sizeof(float) * static_cast<size_t>(d->cout) * d->k * d->k * d->cin;
+  size_t part = wgrad_tc_workspace_bytes(d->n, d->h, d->w, d->cin, d->oh, d->ow, d->cout, d->k, d->stride,
+                                         d->pad, d->ps_r);
+  if (part < full) part = full;
+  float* partials = static_cast<float*>(workspace);
+  float* dbias_tmp = reinterpret_cast<float*>(static_cast<char*>(workspace) + part);
+  float* dot = dbias_tmp + d->cout;
+  const bool need_bias = dbias && !dbias_in;
+  int splits = 1;
+  if (wgrad_tc_supported(d->n, d->h, d->w, d->cin, d->oh, d->ow, d->cout, d->k, d->stride, d->pad,
+                         d->ps_r) && full % 16 == 0) {
+    if (int rc = wgrad_tc_launch(B(x), B(dy), nullptr, need_bias ? dbias_tmp : nullptr, workspace, d->n,
+                                 d->h, d->w, d->cin, d->oh, d->ow, d->cout, d->stride, d->ps_r, S(s),
+                                 &splits))
+      return fail(rc, "conv_wgrad_fused: %s", wgrad_tc_last_error());
+  } else {
+    if (int rc = sisr_conv_wgrad(d, x, dy, partials, need_bias ? dbias_tmp : nullptr, nullptr, s)) return rc;
+  }
+  const float* bsrc = dbias_in ? dbias_in : dbias_tmp;
+  if (full % 16 == 0 && d->cin % 4 == 0)
+    return wrap(weight_grad_reduce_finish(partials, splits, w_orig, u, v, sigma, dw, bsrc, dbias, d->cout,
+                                          d->cin, d->k, d->k, d->ps_r, accumulate, dot, S(s)),
+                "weight_grad_reduce_finish");
+  return wrap(weight_grad_finish(partials, w_orig, u, v, sigma, dw, bsrc, dbias, d->cout, d->cin, d->k,
+                                 d->k, d->ps_r, accumulate, dot, S(s)),
+              "weight_grad_finish");
+}
+int sisr_debug_disable_cooperative(int off) { weight_grad_disable_cooperative(off); return 0; }
+
 // ------------------------------------------------------------------ BatchNorm / activations / pooling
 int sisr_bn_stats(const sisr_bf16* y, long long rows, int c, float* stats, void* s) {
   cudaMemsetAsync(stats, 0, sizeof(float) * 2 * c, S(s));

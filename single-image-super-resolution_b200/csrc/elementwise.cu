@@ -181,25 +181,39 @@ __global__ void col_stats_kernel(const __nv_bfloat16* __restrict__ y, long long 
 }
 
 // ------------------------------------------------------------------ BatchNorm finalize
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int stats_rows, float count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   long long* __restrict__ num_batches, float momentum, float eps,
-                                   int training, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && num_batches) *num_batches += 1;
-  if (c >= C) return;
+// One block per 8 channels: 32 row lanes x 8 channels add the per-CTA partial rows written by the
+// conv epilogue (independent loads), shared-memory tree over the row lanes, 8 threads finalize.
+__global__ void __launch_bounds__(kThreads)
+bn_finalize_kernel(const float* __restrict__ stats, int stats_rows, float count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                   long long* __restrict__ num_batches, float momentum, float eps, int training,
+                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                   float* __restrict__ invstd_out, int C) {
+  __shared__ float s1[32][8], s2[32][8];
+  const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && num_batches) *num_batches += 1;
+  float a1 = 0.f, a2 = 0.f;
+  if (training && c < C) {
+#pragma unroll 5
+    for (int r = rl; r < stats_rows; r += 32) {
+      a1 += stats[static_cast<size_t>(r) * 2 * C + c];
+      a2 += stats[static_cast<size_t>(r) * 2 * C + C + c];
+    }
+  }
+  s1[rl][cl] = a1;
+  s2[rl][cl] = a2;
+  __syncthreads();
+  if (rl != 0 || c >= C) return;
   float mean, var;
   if (training) {
-    float s1 = 0.f, s2 = 0.f;   // add the per-CTA partial rows written by the conv epilogue
-#pragma unroll 4
-    for (int r = 0; r < stats_rows; ++r) {
-      s1 += stats[static_cast<size_t>(r) * 2 * C + c];
-      s2 += stats[static_cast<size_t>(r) * 2 * C + C + c];
+    for (int r = 1; r < 32; ++r) {
+      a1 += s1[r][cl];
+      a2 += s2[r][cl];
     }
-    mean = s1 / count;
-    var = fmaxf(s2 / count - mean * mean, 0.f);
+    mean = a1 / count;
+    var = fmaxf(a2 / count - mean * mean, 0.f);
     const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
@@ -222,24 +236,38 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
                                 const __nv_bfloat16* __restrict__ residual,
                                 __nv_bfloat16* __restrict__ out, long long nvec, int C) {
   const float sl = resolve_slope(act, slope, slope_ptr);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>((i * 8) % C);
-    Vec8 v = load8(y + i * 8);
-    const float4 sc0 = *reinterpret_cast<const float4*>(scale + c0);
-    const float4 sc1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-    const float4 sh0 = *reinterpret_cast<const float4*>(shift + c0);
-    const float4 sh1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-    const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < nvec;
+       i0 += 2 * stride) {
+    Vec8 vv[2], rr[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v.v[j] = act_fwd(fmaf(v.v[j], sc[j], sh[j]), act, sl);
-    if (residual) {
-      const Vec8 r = load8(residual + i * 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v.v[j] += r.v[j];
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        vv[u] = load8(y + i * 8);
+        if (residual) rr[u] = load8(residual + i * 8);
+      }
     }
-    store8(out + i * 8, v);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) break;
+      const int c0 = static_cast<int>((i * 8) % C);
+      const float4 sc0 = *reinterpret_cast<const float4*>(scale + c0);
+      const float4 sc1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+      const float4 sh0 = *reinterpret_cast<const float4*>(shift + c0);
+      const float4 sh1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+      const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+      const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+      Vec8 v = vv[u];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = act_fwd(fmaf(v.v[j], sc[j], sh[j]), act, sl);
+      if (residual) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] += rr[u].v[j];
+      }
+      store8(out + i * 8, v);
+    }
   }
 }
 
@@ -249,6 +277,9 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
 // per-thread partial vectors are combined without atomics: staged as s_red[q][r][C], summed over r
 // by one thread per column, and added to global memory once per column per block.
 constexpr int kRedFloats = 2048;   // rpb * C for every supported C (C % 8 == 0, C <= 2048)
+// (A variant that combined 8 CTAs per thread-block cluster through distributed shared memory before
+// touching global memory was measured 2x SLOWER on the 4.7 MB trunk tensors - cluster scheduling and
+// cluster.sync cost more than the atomics they save - profiles/r1_notes.md.)
 template <int NQ>
 __device__ __forceinline__ void block_col_reduce(const float (&p)[NQ][8], int r, int cv, int rpb, int C,
                                                  bool active, float* s_red, float* const (&out)[NQ]) {
@@ -296,17 +327,29 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
       sc[j] = scale[cv * 8 + j];
       sh[j] = shift[cv * 8 + j];
     }
-    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < M;
-         row += static_cast<long long>(gridDim.x) * rpb) {
-      const Vec8 d = load8(dout + row * C + cv * 8);
-      const Vec8 v = load8(y + row * C + cv * 8);
+    // 2 rows per trip: 4 independent 16-byte loads in flight per thread
+    const long long stride = static_cast<long long>(gridDim.x) * rpb;
+    for (long long row0 = static_cast<long long>(blockIdx.x) * rpb + r; row0 < M; row0 += 2 * stride) {
+      Vec8 d[2], v[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(v.v[j], sc[j], sh[j]);
-        const float g = d.v[j] * act_grad(z, act, sl);
-        p[0][j] += g;
-        p[1][j] += g * (v.v[j] - mu[j]) * is[j];
-        if (act == ACT_PRELU) sa += d.v[j] * fminf(z, 0.f);
+      for (int u = 0; u < 2; ++u) {
+        const long long row = row0 + u * stride;
+        if (row < M) {
+          d[u] = load8(dout + row * C + cv * 8);
+          v[u] = load8(y + row * C + cv * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (row0 + u * stride >= M) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(v[u].v[j], sc[j], sh[j]);
+          const float g = d[u].v[j] * act_grad(z, act, sl);
+          p[0][j] += g;
+          p[1][j] += g * (v[u].v[j] - mu[j]) * is[j];
+          if (act == ACT_PRELU) sa += d[u].v[j] * fminf(z, 0.f);
+        }
       }
     }
   }
@@ -323,6 +366,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
     }
   }
 }
+
 
 // dy = gamma*invstd * (g - sum_g/count - xhat * sum_gx/count);  colsum[c] += sum_rows dy (as stored)
 __global__ void __launch_bounds__(kThreads)
@@ -351,20 +395,32 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
       k1[j] = sums[c] * inv_count;
       k2[j] = sums[C + c] * inv_count;
     }
-    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < M;
-         row += static_cast<long long>(gridDim.x) * rpb) {
-      const Vec8 d = load8(dout + row * C + cv * 8);
-      const Vec8 v = load8(y + row * C + cv * 8);
-      Vec8 o;
+    const long long stride = static_cast<long long>(gridDim.x) * rpb;
+    for (long long row0 = static_cast<long long>(blockIdx.x) * rpb + r; row0 < M; row0 += 2 * stride) {
+      Vec8 d[2], v[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(v.v[j], sc[j], sh[j]);
-        const float g = d.v[j] * act_grad(z, act, sl);
-        const float xh = (v.v[j] - mu[j]) * is[j];
-        o.v[j] = bf16_round(sc[j] * (g - k1[j] - xh * k2[j]));
-        p[0][j] += o.v[j];
+      for (int u = 0; u < 2; ++u) {
+        const long long row = row0 + u * stride;
+        if (row < M) {
+          d[u] = load8(dout + row * C + cv * 8);
+          v[u] = load8(y + row * C + cv * 8);
+        }
       }
-      store8(dy + row * C + cv * 8, o);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const long long row = row0 + u * stride;
+        if (row >= M) break;
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(v[u].v[j], sc[j], sh[j]);
+          const float g = d[u].v[j] * act_grad(z, act, sl);
+          const float xh = (v[u].v[j] - mu[j]) * is[j];
+          o.v[j] = bf16_round(sc[j] * (g - k1[j] - xh * k2[j]));
+          p[0][j] += o.v[j];
+        }
+        store8(dy + row * C + cv * 8, o);
+      }
     }
   }
   if (colsum) {
@@ -554,6 +610,7 @@ __global__ void bce_bwd_kernel(const float* __restrict__ p, int n, float target,
 
 int check() { return cudaGetLastError() == cudaSuccess ? 0 : 4; }
 
+
 }  // namespace
 
 int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int N, int C, int H, int W,
@@ -596,7 +653,7 @@ int bn_finalize(const float* stats, int stats_rows, float count, const float* ga
                 float* running_mean, float* running_var, long long* num_batches, float momentum,
                 float eps, int training, float* scale, float* shift, float* mean, float* invstd, int C,
                 cudaStream_t s) {
-  bn_finalize_kernel<<<(C + 31) / 32, 32, 0, s>>>(stats, stats_rows, count, gamma, beta, running_mean,
+  bn_finalize_kernel<<<(C + 7) / 8, kThreads, 0, s>>>(stats, stats_rows, count, gamma, beta, running_mean,
                                                      running_var, num_batches, momentum, eps, training,
                                                      scale, shift, mean, invstd, C);
   return check();
@@ -606,7 +663,7 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, int
              int C, cudaStream_t s) {
   if (C % 8) return 1;
   const long long nvec = M * C / 8;
-  bn_apply_kernel<<<grid_for(nvec, kThreads), kThreads, 0, s>>>(y, scale, shift, act, slope, slope_ptr,
+  bn_apply_kernel<<<grid_for(nvec, 2 * kThreads, 148 * 8), kThreads, 0, s>>>(y, scale, shift, act, slope, slope_ptr,
                                                                 residual, out, nvec, C);
   return check();
 }

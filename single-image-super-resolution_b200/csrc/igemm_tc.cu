@@ -330,7 +330,8 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
   return 0;
 }
 
-bool g_force_im2col = false;   // igemm_force_im2col(): A/B switch for benchmarks and tests
+bool g_force_im2col = true;    // tiled-mode A boxes measured no faster than im2col mode (same L2 traffic)
+                               // and their tile counts quantise worse; igemm_force_im2col(0) enables them
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {

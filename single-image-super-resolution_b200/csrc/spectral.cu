@@ -4,6 +4,7 @@
 // weight gradient back to the fp32 master layout including the gradient through sigma.
 #include "spectral.h"
 
+#include <cooperative_groups.h>
 #include <stdio.h>
 
 namespace sisr {
@@ -250,14 +251,100 @@ weight_prep_batched_kernel(const __grid_constant__ PrepTable tab) {
   }
 }
 
+// Split-K reduce + spectral-norm gradient + layout change in ONE cooperative kernel:
+//   phase 1: G = sum_k partial_k (prepared layout [co'][tap][ci]); dw[co][ci][tap] (+)= G / sigma;
+//            dot += <G, W_orig>; bias gradient copied
+//   grid sync
+//   phase 2: dw -= dot / sigma^2 * u v^T            (gradient through sigma, u and v constant)
+// Block = 16 float4 columns x 16 split lanes.  phases: 3 = both (cooperative launch), 1 / 2 = one
+// phase per ordinary launch.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_finish_kernel(const float* __restrict__ partials, int splits, const float* __restrict__ w,
+                           const float* __restrict__ u, const float* __restrict__ v,
+                           const float* __restrict__ sigma, float* __restrict__ dot,
+                           float* __restrict__ dw, const float* __restrict__ dbias_perm,
+                           float* __restrict__ dbias, int Cout, int Cin, int taps, int ps_r,
+                           int accumulate, int phases) {
+  __shared__ float4 s_part[16][16];
+  __shared__ float s_dot[16];
+  const long long total = static_cast<long long>(Cout) * taps * Cin;
+  const long long total4 = total / 4;
+  const float inv = sigma ? 1.f / *sigma : 1.f;
+  if (phases & 1) {
+    const int x = threadIdx.x & 15, y = threadIdx.x >> 4;
+    float dacc = 0.f;
+    for (long long c0 = static_cast<long long>(blockIdx.x) * 16; c0 < total4;
+         c0 += static_cast<long long>(gridDim.x) * 16) {
+      const long long i4 = c0 + x;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i4 < total4) {
+        const float4* p = reinterpret_cast<const float4*>(partials) + i4;
+#pragma unroll 4
+        for (int k = y; k < splits; k += 16) {
+          const float4 t = __ldg(p + static_cast<long long>(k) * total4);
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+      }
+      s_part[y][x] = acc;
+      __syncthreads();
+      if (y == 0 && i4 < total4) {
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {
+          const float4 t = s_part[k][x];
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        const long long i = i4 * 4;
+        const int ci = static_cast<int>(i % Cin);
+        const int tap = static_cast<int>((i / Cin) % taps);
+        const int cop = static_cast<int>(i / (static_cast<long long>(Cin) * taps));
+        const int co = unpermute_row(cop, Cout, ps_r);
+        const size_t o = (static_cast<size_t>(co) * Cin + ci) * taps + tap;
+        const float g[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const size_t oe = o + static_cast<size_t>(e) * taps;
+          if (sigma) dacc = fmaf(g[e], w[oe], dacc);
+          dw[oe] = accumulate ? dw[oe] + g[e] * inv : g[e] * inv;
+        }
+        if (dbias && tap == 0 && ci == 0)
+          dbias[co] = accumulate ? dbias[co] + dbias_perm[cop] : dbias_perm[cop];
+      }
+      __syncthreads();
+    }
+    if (sigma) {
+      if (y == 0) s_dot[x] = dacc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 16; ++k) t += s_dot[k];
+        atomicAdd(dot, t);
+      }
+    }
+  }
+  if (phases == 3) cooperative_groups::this_grid().sync();
+  if ((phases & 2) && sigma) {
+    const float coef = (*reinterpret_cast<volatile float*>(dot)) * inv * inv;
+    const int K = Cin * taps;
+    for (long long o = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; o < total;
+         o += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int co = static_cast<int>(o / K);
+      const int k = static_cast<int>(o - static_cast<long long>(co) * K);
+      dw[o] -= coef * u[co] * v[k];
+    }
+  }
+}
+
 inline int grid_for(long long work) {
   long long b = (work + kThreads - 1) / kThreads;
   if (b > 148 * 8) b = 148 * 8;
   return static_cast<int>(b < 1 ? 1 : b);
 }
 int check() { return cudaGetLastError() == cudaSuccess ? 0 : 4; }
+bool g_no_coop = false;
 
 }  // namespace
+
+void weight_grad_disable_cooperative(int off) { g_no_coop = off != 0; }
 
 size_t sn_workspace_floats(int Cout, int K) { return static_cast<size_t>(K) + Cout + 4; }
 
@@ -324,6 +411,49 @@ int weight_prep(const float* w, const float* sigma, const float* bias, __nv_bflo
   const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
   weight_prep_kernel<<<grid_for(total), kThreads, 0, s>>>(w, sigma, bias, wf, wd, bias_perm, Cout, Cin,
                                                           KH, KW, ps_r);
+  return check();
+}
+
+int weight_grad_reduce_finish(const float* partials, int splits, const float* w, const float* u,
+                              const float* v, const float* sigma, float* dw, const float* dbias_perm,
+                              float* dbias, int Cout, int Cin, int KH, int KW, int ps_r, int accumulate,
+                              float* dot, cudaStream_t s) {
+  const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+  if (total % 4 || Cin % 4) return 1;
+  int taps = KH * KW;
+  if (sigma) cudaMemsetAsync(dot, 0, sizeof(float), s);
+  static int max_coop_blocks = -1;   // co-resident blocks of the cooperative kernel (0: unsupported)
+  if (max_coop_blocks < 0) {
+    int dev = 0, sms = 0, coop = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wgrad_reduce_finish_kernel, 256, 0);
+    max_coop_blocks = (coop && per_sm > 0 && sms > 0) ? sms * (per_sm < 4 ? per_sm : 4) : 0;
+    cudaGetLastError();
+  }
+  long long want = (total / 4 + 15) / 16;
+  if (!sigma) {   // no gradient through sigma: phase 1 alone is complete
+    const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+    wgrad_reduce_finish_kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw,
+                                                     dbias_perm, dbias, Cout, Cin, taps, ps_r,
+                                                     accumulate, 1);
+    return check();
+  }
+  if (max_coop_blocks > 0 && !g_no_coop) {
+    const int grid = static_cast<int>(want < max_coop_blocks ? want : max_coop_blocks);
+    int phases = 3;
+    void* args[] = {&partials, &splits, &w, &u, &v, &sigma, &dot, &dw, &dbias_perm, &dbias,
+                    &Cout, &Cin, &taps, &ps_r, &accumulate, &phases};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(wgrad_reduce_finish_kernel),
+                                                dim3(grid), dim3(256), args, 0, s);
+    return e == cudaSuccess ? 0 : 4;
+  }
+  const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+  wgrad_reduce_finish_kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw, dbias_perm,
+                                                   dbias, Cout, Cin, taps, ps_r, accumulate, 1);
+  wgrad_reduce_finish_kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw, dbias_perm,
+                                                   dbias, Cout, Cin, taps, ps_r, accumulate, 2);
   return check();
 }
 

@@ -61,4 +61,12 @@ int weight_grad_finish(const float* gp, const float* w, const float* u, const fl
                        const float* sigma, float* dw, const float* dbias_perm, float* dbias, int Cout,
                        int Cin, int KH, int KW, int ps_r, int accumulate, float* ws, cudaStream_t s);
 
+// Fused split-K reduce + finish: partials [splits][Cout'][kh][kw][Cin] fp32 -> dw [Cout][Cin][kh][kw]
+// (one cooperative kernel when spectral norm is on).  dot: one float of scratch.
+int weight_grad_reduce_finish(const float* partials, int splits, const float* w, const float* u,
+                              const float* v, const float* sigma, float* dw, const float* dbias_perm,
+                              float* dbias, int Cout, int Cin, int KH, int KW, int ps_r, int accumulate,
+                              float* dot, cudaStream_t s);
+void weight_grad_disable_cooperative(int off);   // 1: two ordinary launches instead (debug / fallback)
+
 }  // namespace sisr

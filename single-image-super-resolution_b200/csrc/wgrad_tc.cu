@@ -258,17 +258,19 @@ size_t wgrad_tc_workspace_bytes(int n, int h, int w, int cin, int oh, int ow, in
                                 int stride, int pad, int ps_r) {
   if (!wgrad_tc_supported(n, h, w, cin, oh, ow, cout, k, stride, pad, ps_r)) return 0;
   const Plan pl = make_plan(n, oh, ow, cin, cout);
-  return pl.splits > 1 ? static_cast<size_t>(pl.splits) * cout * 9 * cin * sizeof(float) : 0;
+  return static_cast<size_t>(pl.splits) * cout * 9 * cin * sizeof(float);
 }
 
 int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, float* dbias,
                     void* workspace, int n, int h, int w, int cin, int oh, int ow, int cout, int stride,
-                    int ps_r, cudaStream_t s) {
+                    int ps_r, cudaStream_t s, int* splits_out) {
   const Plan pl = make_plan(n, oh, ow, cin, cout);
-  if (pl.splits > 1 && !workspace) {
+  const bool keep_partials = g == nullptr;   // caller reduces (weight_grad_reduce_finish)
+  if ((pl.splits > 1 || keep_partials) && !workspace) {
     snprintf(g_err, sizeof g_err, "wgrad: split-K workspace missing");
     return 1;
   }
+  if (splits_out) *splits_out = pl.splits;
   CUtensorMap tx, tdy;
   if (make_tmap_im2col_nhwc_bf16(&tx, x, n, h, w, cin, -1, -1, -1, -1, 64, kPix, stride)) {
     snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
@@ -290,7 +292,7 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
   p.ci_blocks = cin / 64; p.co_blocks = cout / 64;
   p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.total_kb = pl.total_kb;
   p.Cin = cin; p.Cout = cout; p.ps = ps;
-  p.out = pl.splits > 1 ? static_cast<float*>(workspace) : g;
+  p.out = (pl.splits > 1 || keep_partials) ? static_cast<float*>(workspace) : g;
   const int smem_bytes = kStages * kStageBytes + 1024;
   static bool configured = false;
   if (!configured) {
@@ -304,7 +306,7 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
   }
   const int grid = pl.tiles * pl.splits;
   wgrad_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(tx, tdy, p);
-  if (pl.splits > 1) {
+  if (pl.splits > 1 && !keep_partials) {
     const long long total4 = static_cast<long long>(cout) * 9 * cin / 4;
     splitk_reduce_kernel<<<static_cast<int>((total4 + 15) / 16), 256, 0, s>>>(
         static_cast<const float*>(workspace), g, total4, pl.splits);

@@ -10,10 +10,12 @@ bool wgrad_tc_supported(int n, int h, int w, int cin, int oh, int ow, int cout, 
                         int pad, int ps_r);
 size_t wgrad_tc_workspace_bytes(int n, int h, int w, int cin, int oh, int ow, int cout, int k,
                                 int stride, int pad, int ps_r);
-// g: fp32 [cout', 3, 3, cin] overwritten; dbias: fp32 [cout'] or null.
+// g: fp32 [cout', 3, 3, cin] overwritten; dbias: fp32 [cout'] or null.  g == nullptr: the split-K
+// partials [splits][cout'][3][3][cin] are left in `workspace` (wgrad_tc_workspace_bytes) for the caller
+// to reduce; *splits_out receives their number.
 int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, float* dbias,
                     void* workspace, int n, int h, int w, int cin, int oh, int ow, int cout, int stride,
-                    int ps_r, cudaStream_t s);
+                    int ps_r, cudaStream_t s, int* splits_out = nullptr);
 const char* wgrad_tc_last_error();
 
 }  // namespace sisr

@@ -343,18 +343,12 @@ class Conv2dFn(torch.autograd.Function):
             call("sisr_conv_dgrad", d, dpre, wf, wd, dx, st)
         dw = db = None
         if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not ctx.skip_params:
-            gp = torch.empty((cout, k, k, cin), dtype=torch.float32, device=dev)
-            dbp = torch.empty(cout, dtype=torch.float32, device=dev)
-            nbytes = query("sisr_conv_wgrad_workspace_bytes", d)
-            ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dev)
-            call("sisr_conv_wgrad", d, x, dpre, gp, dbp if colsum is None else None, ws, st)
-            if colsum is not None:      # bias gradient already reduced by the kernel that wrote dpre
-                dbp = colsum
+            nbytes = query("sisr_conv_wgrad_fused_workspace_bytes", d)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             dw = torch.empty_like(weight)
             db = torch.empty(cout, dtype=torch.float32, device=dev)
-            ws2 = torch.empty(4, dtype=torch.float32, device=dev)
-            call("sisr_weight_grad_finish", gp, weight, u, v, sigma if ctx.has_sn else None, dw, dbp, db,
-                 cout, cin, k, cfg.ps_r, 0, ws2, st)
+            call("sisr_conv_wgrad_fused", d, x, dpre, weight, u, v, sigma if ctx.has_sn else None, dw,
+                 colsum, db, 0, ws, st)
             if not ctx.needs_input_grad[1]:
                 dw = None
             if not ctx.needs_input_grad[2]:
