@@ -42,8 +42,12 @@ const char* sisr_last_error(void);
 int sisr_abi_version(void);
 /* number of partial-sum rows of a `stats` buffer (= SM count: one row per persistent CTA) */
 int sisr_stats_rows(void);
-/* debug / A-B timing: 1 = always feed the conv engine with im2col-mode TMA (never the tiled-mode boxes) */
-int sisr_debug_force_im2col(int on);
+/* debug / A-B timing: conv engine A-operand feed: 0 = im2col-mode TMA only, 1 = cost model (default),
+ * 2 = halo tiles whenever the geometry allows */
+int sisr_debug_halo_mode(int mode);
+/* debug / A-B timing: 0 = layers with cout <= 128 use the 128-pixel x cout tiles instead of the
+ * 128-channel x 256-pixel (transposed) tiles */
+int sisr_debug_transposed(int on);
 /* 1 if the tcgen05 implicit-GEMM engine takes this fprop/dgrad shape, 0 if the CUDA-core kernel does */
 int sisr_conv_uses_tensor_cores(const sisr_conv_desc* d);
 

@@ -320,7 +320,25 @@ int main(int argc, char** argv) {
       {"c256_512_6x6_n8", 8, 6, 6, 256, 512, 1, 0, ACT_RELU, 0},
       {"c128_256_s2_12x12_n8", 8, 12, 12, 128, 256, 2, 0, ACT_NONE, 1},
   };
+  igemm_set_halo_mode(0);
+  igemm_set_transposed(1);
+  printf("-- default engine (transposed tiles for Cout <= 128)\n");
   for (const auto& cc : convs) fails += run_conv(cc, false);
+  igemm_set_transposed(0);
+  printf("-- im2col-fed kernel\n");
+  for (const auto& cc : convs) fails += run_conv(cc, false);
+  igemm_set_halo_mode(2);
+  printf("-- halo-fed kernel wherever the geometry allows\n");
+  const ConvCase halo_extra[] = {
+      {"h_c64_48x48_n2", 2, 48, 48, 64, 64, 1, 0, ACT_NONE, 1},
+      {"h_c64_128_32x32_n2", 2, 32, 32, 64, 128, 1, 0, ACT_LEAKY, 1},
+      {"h_c128_256_24x24_n3", 3, 24, 24, 128, 256, 1, 0, ACT_RELU, 0},
+      {"h_c64_9x7_n2", 2, 9, 7, 64, 64, 1, 0, ACT_NONE, 1},
+      {"h_c256_256_96x96_n1", 1, 96, 96, 256, 256, 1, 0, ACT_RELU, 0},
+  };
+  for (const auto& cc : convs) fails += run_conv(cc, false);
+  for (const auto& cc : halo_extra) fails += run_conv(cc, false);
+  igemm_set_halo_mode(1);
   if (argc > 1) {
     const ConvCase big[] = {
         {"trunk_c64_24x24_n64", 64, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},

@@ -1,15 +1,26 @@
 // tcgen05 implicit-GEMM convolution engine for sm_100a.
 //
-//   warp 0      : TMA producer  (im2col-mode loads of the activation tile, tiled loads of weights)
+//   warp 0      : TMA producer
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
 //   warps 2..5  : epilogue (tcgen05.ld -> bias / activation / BN statistics -> bf16 NHWC store)
 //
-// Persistent: one CTA per SM walks the 128 x BN output tiles (tile = blockIdx.x + i * gridDim.x);
-// the K loop of a tile runs over (tap, 64-channel block).  The TMEM accumulator is double
-// buffered (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1 and
-// barrier / TMEM set-up is paid once per SM instead of once per tile.
-// A tile : 128 pixels x 64 channels bf16 = 16 KB, 128 B rows, hardware 128 B swizzle (K-major).
-// B tile : BN rows x 64 k bf16, same layout.  Accumulator: 128 lanes x BN fp32 columns in TMEM.
+// Persistent: one CTA per SM walks the 128 x BN output tiles (tile = blockIdx.x + i * gridDim.x).
+// The TMEM accumulator is double buffered (2 x BN columns), so the epilogue of tile i overlaps the
+// main loop of tile i+1 and barrier / TMEM set-up is paid once per SM instead of once per tile.
+// B tile : BN rows x 64 k bf16, 128 B rows, hardware 128 B swizzle (K-major).
+//
+// Two ways of feeding the A (activation) operand:
+//   * igemm_tc_kernel   - im2col-mode TMA: one 128 pixel x 64 channel tile per (tap, channel block).
+//     Handles every geometry (stride 2, dgrad through PixelShuffle, parity-split dgrad) but moves
+//     9 x 16 KB of activations per 64 channels of K, which makes the thin layers L2-bandwidth bound.
+//   * igemm_halo_kernel - stride-1 same-size 3x3 convs: an M tile is R rows x TW columns of one
+//     image; ONE tiled-mode TMA box {64 ch, TW+2, R+2} (zero fill outside the image = padding)
+//     brings the tile with its halo, and the nine taps are nine UMMA descriptors into that box:
+//     accumulator row i = r*(TW+2)+c reads box row i + dy*(TW+2) + dx (a plain start-address shift,
+//     the 128 B swizzle is a function of the absolute shared-memory address - csrc/probe_shift.cu).
+//     The two halo columns of every row produce rows that are discarded (<= 10 % of the MMA work) and
+//     the activation traffic drops 9x.  When the whole weight matrix is 9 B tiles (Cin = 64, one N
+//     tile) it is loaded once per CTA and stays resident.
 #include <stdio.h>
 
 #include "igemm.h"
@@ -24,17 +35,10 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kThreads = 192;
 constexpr int kATileBytes = kBM * kBK * 2;
+constexpr int kHaloABytes = 32768;   // one halo box buffer (two of them: double buffered)
+constexpr int kMaxCout = 512;        // per-CTA bias / BN statistics arrays
 
-constexpr int kMaxCout = 512;   // per-CTA BN statistics accumulator
-
-struct KParams {
-  int M, GH, GW, trav_stride, lower_w, lower_h;
-  int cin_blocks, num_taps, n_tiles, m_tiles;
-  // tiled A loads (stride-1 same-size convs): an M tile is a TH x TW pixel rectangle of one image,
-  // fetched per tap as ONE tiled-mode TMA box {64 ch, TW, TH} shifted by the tap offset (zero fill
-  // outside the image = conv padding); tiled = 0: im2col-mode TMA over 128 consecutive positions
-  int tiled, TW, TH, tiles_w, tiles_hw, a_bytes;
-  IgemmTaps taps;
+struct EpiParams {
   __nv_bfloat16* out;
   int OH, OW, ldc, osy, osx, opy, opx, ps_c;
   const float* bias;
@@ -43,6 +47,37 @@ struct KParams {
   const float* slope_ptr;
   float* stats;
   int stats_rows;
+};
+
+struct KParams {
+  int M, GH, GW, trav_stride, lower_w, lower_h;
+  int cin_blocks, num_taps, n_tiles, m_tiles;
+  IgemmTaps taps;
+  EpiParams e;
+};
+
+struct HParams {
+  int H, W;                 // image = output size
+  int TW, R, PW;            // tile columns / rows, box pitch PW = TW + 2
+  int tiles_w, tiles_hw, m_tiles, n_tiles;
+  int cin_blocks, a_bytes;
+  int resident;             // weights stay in shared memory (cin_blocks == 1, n_tiles == 1)
+  int shift[9];             // box row shift of each tap
+  int k_off[9];             // first weight column of each tap
+  EpiParams e;
+};
+
+// Transposed tiles (Cout <= 128): the WEIGHTS are the M operand (128 rows, rows >= Cout zero-filled by
+// TMA) and 256 PIXELS are the N operand.  Measured: a tcgen05.mma with M = 128 costs >= 128 cycles per
+// K = 16 step whatever N is (the A operand is fetched from shared memory row by row), so a 128 pixel x
+// 64 channel instruction runs at 25 % of the tensor peak (ncu: V 64->64 @96, 514 cycles per 64-wide
+// k-block, profiles/r1_notes.md).  With the pixels on the N side every instruction covers 256 pixels.
+struct TParams {
+  int M, GH, GW, trav_stride, lower_w, lower_h;
+  int cin_blocks, num_taps, p_tiles, cout;
+  int flat;   // output pixel index == accumulator column index (no parity / stride remap)
+  IgemmTaps taps;
+  EpiParams e;
 };
 
 template <int BN>
@@ -69,6 +104,85 @@ __device__ __forceinline__ float column_sums_32x32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// Epilogue of one 128 x BN tile for one warp (32 accumulator rows): this thread owns output pixel
+// (n_img, gh, gw) (ignored when !valid).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t tmem_tile, int quad, int lane,
+                                              int n0, int cout, int n_img, int gh, int gw, bool valid,
+                                              float slope, const float* s_bias, float* s_stats) {
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t raw[32];
+    tmem_ld_32x32(tmem_tile + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, raw);
+    tmem_ld_wait();
+    const int ncol = n0 + c * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float x = __uint_as_float(raw[i]) + s_bias[ncol + i];
+      if (e.act != ACT_NONE) x = x > 0.f ? x : x * slope;
+      v[i] = x;
+    }
+    int oy, ox, ch;
+    if (e.ps_c > 0) {
+      const int sub = ncol / e.ps_c;
+      ch = ncol - sub * e.ps_c;
+      oy = gh * 2 + (sub >> 1);
+      ox = gw * 2 + (sub & 1);
+    } else {
+      ch = ncol;
+      oy = gh * e.osy + e.opy;
+      ox = gw * e.osx + e.opx;
+    }
+    uint32_t packed[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    if (valid) {
+      __nv_bfloat16* dst = e.out + (static_cast<size_t>(n_img * e.OH + oy) * e.OW + ox) * e.ldc + ch;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    }
+    if (e.stats) {
+      // statistics of the values as stored (bf16-rounded), invalid rows contribute zero
+      float q[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&packed[i]);
+        const float a = valid ? __low2float(h) : 0.f;
+        const float b = valid ? __high2float(h) : 0.f;
+        v[2 * i] = a;
+        v[2 * i + 1] = b;
+        q[2 * i] = a * a;
+        q[2 * i + 1] = b * b;
+      }
+      const float cs = column_sums_32x32(v, lane);
+      const float cq = column_sums_32x32(q, lane);
+      atomicAdd(&s_stats[ncol + lane], cs);
+      atomicAdd(&s_stats[cout + ncol + lane], cq);
+    }
+  }
+}
+
+// per-CTA partial BN sums -> row blockIdx.x of the stats buffer (plain stores; bn_finalize adds rows)
+__device__ __forceinline__ void flush_stats(const EpiParams& e, const float* s_stats, int cout) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  float* mine = e.stats + static_cast<size_t>(blockIdx.x) * 2 * cout;
+  for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) mine[i] = s_stats[i];
+  for (int r = gridDim.x + blockIdx.x; r < e.stats_rows; r += gridDim.x) {
+    float* z = e.stats + static_cast<size_t>(r) * 2 * cout;
+    for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) z[i] = 0.f;
+  }
+}
+
+__device__ __forceinline__ float resolve_slope(const EpiParams& e) {
+  if (e.act == ACT_PRELU) return __ldg(e.slope_ptr);
+  if (e.act == ACT_RELU) return 0.f;
+  return e.slope;
+}
+
+// ------------------------------------------------------------------ im2col-fed kernel
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -110,8 +224,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     tmem_relinquish();
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < cout; i += 128) s_bias[i] = p.bias ? p.bias[i] : 0.f;
-    if (p.stats)
+    for (int i = threadIdx.x - 64; i < cout; i += 128) s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
+    if (p.e.stats)
       for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) s_stats[i] = 0.f;
   }
   tc_fence_before();
@@ -125,21 +239,12 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int hw = p.GH * p.GW;
       uint32_t kbg = 0;   // k-block counter across tiles (pipeline stage / phase)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tile_m = tile / p.n_tiles;
+        const int m0 = (tile / p.n_tiles) * kBM;
         const int n0 = (tile % p.n_tiles) * BN;
-        int n_img, gh, gw;
-        if (p.tiled) {
-          n_img = tile_m / p.tiles_hw;
-          const int r2 = tile_m - n_img * p.tiles_hw;
-          gh = (r2 / p.tiles_w) * p.TH;
-          gw = (r2 % p.tiles_w) * p.TW;
-        } else {
-          const int m0 = tile_m * kBM;
-          n_img = m0 / hw;
-          const int rem = m0 - n_img * hw;
-          gh = rem / p.GW;
-          gw = rem - gh * p.GW;
-        }
+        const int n_img = m0 / hw;
+        const int rem = m0 - n_img * hw;
+        const int gh = rem / p.GW;
+        const int gw = rem - gh * p.GW;
         const int cw = gw * p.trav_stride + p.lower_w;
         const int ch = gh * p.trav_stride + p.lower_h;
         for (int tap = 0; tap < p.num_taps; ++tap) {
@@ -148,15 +253,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t round = kbg / STAGES;
             mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);
             const uint32_t fb = smem_u32(&full_bar[s]);
-            mbar_expect_tx(fb, p.a_bytes + L::kBTileBytes);
+            mbar_expect_tx(fb, L::kStageBytes);
             const uint32_t a_dst = smem_u32(smem + s * L::kStageBytes);
             const uint32_t b_dst = a_dst + kATileBytes;
-            if (p.tiled)
-              tma_load_4d(a_dst, &tmap_a, fb, cb * kBK, cw + p.taps.off_w[tap], ch + p.taps.off_h[tap],
-                          n_img);
-            else
-              tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * kBK, cw, ch, n_img, p.taps.off_w[tap],
-                                 p.taps.off_h[tap]);
+            tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * kBK, cw, ch, n_img, p.taps.off_w[tap],
+                               p.taps.off_h[tap]);
             tma_load_2d(b_dst, &tmap_b, fb, p.taps.k_off[tap] + cb * kBK, n0);
           }
         }
@@ -195,108 +296,28 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ------------------------------------------------------------ epilogue
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int hw = p.GH * p.GW;
-    float slope = p.slope;
-    if (p.act == ACT_PRELU) slope = __ldg(p.slope_ptr);
-    if (p.act == ACT_RELU) slope = 0.f;
+    const float slope = resolve_slope(p.e);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, use = it >> 1;
-      const int tile_m = tile / p.n_tiles;
       const int n0 = (tile % p.n_tiles) * BN;
-      int n_img, gh, gw;
-      bool valid;
-      if (p.tiled) {
-        const int r = quad * 32 + lane;
-        n_img = tile_m / p.tiles_hw;
-        const int r2 = tile_m - n_img * p.tiles_hw;
-        const int th = r / p.TW;
-        gh = (r2 / p.tiles_w) * p.TH + th;
-        gw = (r2 % p.tiles_w) * p.TW + (r - th * p.TW);
-        valid = th < p.TH && gh < p.GH && gw < p.GW;
-        if (!valid) gh = gw = 0;
-      } else {
-        const int row = tile_m * kBM + quad * 32 + lane;
-        valid = row < p.M;
-        const int rr = valid ? row : 0;
-        n_img = rr / hw;
-        const int rem = rr - n_img * hw;
-        gh = rem / p.GW;
-        gw = rem - gh * p.GW;
-      }
-
+      const int row = (tile / p.n_tiles) * kBM + quad * 32 + lane;
+      const bool valid = row < p.M;
+      const int rr = valid ? row : 0;
+      const int n_img = rr / hw;
+      const int rem = rr - n_img * hw;
+      const int gh = rem / p.GW;
+      const int gw = rem - gh * p.GW;
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
       tc_fence_after();
-
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, raw);
-        tmem_ld_wait();
-        const int ncol = n0 + c * 32;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(raw[i]) + s_bias[ncol + i];
-          if (p.act != ACT_NONE) x = x > 0.f ? x : x * slope;
-          v[i] = x;
-        }
-        // destination of this 32-channel chunk
-        int oy, ox, ch;
-        if (p.ps_c > 0) {
-          const int sub = ncol / p.ps_c;
-          ch = ncol - sub * p.ps_c;
-          oy = gh * 2 + (sub >> 1);
-          ox = gw * 2 + (sub & 1);
-        } else {
-          ch = ncol;
-          oy = gh * p.osy + p.opy;
-          ox = gw * p.osx + p.opx;
-        }
-        uint32_t packed[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        if (valid) {
-          __nv_bfloat16* dst =
-              p.out + (static_cast<size_t>(n_img * p.OH + oy) * p.OW + ox) * p.ldc + ch;
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-        }
-        if (p.stats) {
-          // statistics of the values as stored (bf16-rounded), invalid rows contribute zero
-          float q[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&packed[i]);
-            const float a = valid ? __low2float(h) : 0.f;
-            const float b = valid ? __high2float(h) : 0.f;
-            v[2 * i] = a;
-            v[2 * i + 1] = b;
-            q[2 * i] = a * a;
-            q[2 * i + 1] = b * b;
-          }
-          const float cs = column_sums_32x32(v, lane);
-          const float cq = column_sums_32x32(q, lane);
-          atomicAdd(&s_stats[ncol + lane], cs);
-          atomicAdd(&s_stats[cout + ncol + lane], cq);
-        }
-      }
+      epilogue_tile<BN>(p.e, tmem_base + acc * BN, quad, lane, n0, cout, n_img, gh, gw, valid, slope,
+                        s_bias, s_stats);
       // this warp's TMEM reads of the buffer are complete: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
     }
-    if (p.stats) {
-      // per-CTA partial sums, plain stores (no contended atomics); bn_finalize adds the rows
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* mine = p.stats + static_cast<size_t>(blockIdx.x) * 2 * cout;
-      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) mine[i] = s_stats[i];
-      for (int r = gridDim.x + blockIdx.x; r < p.stats_rows; r += gridDim.x) {
-        float* z = p.stats + static_cast<size_t>(r) * 2 * cout;
-        for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) z[i] = 0.f;
-      }
-    }
+    if (p.e.stats) flush_stats(p.e, s_stats, cout);
   }
 
   tc_fence_before();
@@ -307,21 +328,404 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ transposed kernel (Cout <= 128)
+constexpr int kTP = 256;                          // pixels per tile (UMMA N)
+constexpr int kTWBytes = 128 * kBK * 2;           // weight tile: 128 rows x 64 k
+constexpr int kTPBytes = kTP * kBK * 2;           // pixel tile: 256 rows x 64 k
+constexpr int kTStage = kTWBytes + kTPBytes;      // 48 KB
+constexpr int kTThreads = 320;                    // TMA warp + MMA warp + 8 epilogue warps
+
+template <int STAGES>
+__global__ void __launch_bounds__(kTThreads, 1)
+igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constant__ CUtensorMap tmap_w,
+               const TParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) uint32_t s_stage[2][32 * (64 + 16)];   // [half][32 px][cout/2 + 16 words]
+  __shared__ float s_sum[2 * 128];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = p.num_taps * p.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_px);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 8);   // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), 2 * kTP);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int hw = p.GH * p.GW;
+      uint32_t kbg = 0;
+      for (int tile = blockIdx.x; tile < p.p_tiles; tile += gridDim.x) {
+        const int m0 = tile * kTP;
+        const int n_img = m0 / hw;
+        const int rem = m0 - n_img * hw;
+        const int gh = rem / p.GW;
+        const int gw = rem - gh * p.GW;
+        const int cw = gw * p.trav_stride + p.lower_w;
+        const int ch = gh * p.trav_stride + p.lower_h;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          for (int cb = 0; cb < p.cin_blocks; ++cb, ++kbg) {
+            const uint32_t s = kbg % STAGES;
+            mbar_wait(smem_u32(&empty_bar[s]), ((kbg / STAGES) & 1) ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            mbar_expect_tx(fb, kTStage);
+            const uint32_t w_dst = smem_u32(smem + s * kTStage);
+            tma_load_2d(w_dst, &tmap_w, fb, p.taps.k_off[tap] + cb * kBK, 0);
+            tma_load_im2col_4d(w_dst + kTWBytes, &tmap_px, fb, cb * kBK, cw, ch, n_img,
+                               p.taps.off_w[tap], p.taps.off_h[tap]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: D[co, px] += W * X^T
+    constexpr uint32_t idesc = umma_idesc_bf16(128, kTP, 0, 0);
+    uint32_t kbg = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.p_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, use = it >> 1;
+      mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kTP;
+      for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+        const uint32_t s = kbg % STAGES;
+        mbar_wait(smem_u32(&full_bar[s]), (kbg / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t w_addr = smem_u32(smem + s * kTStage);
+          const uint32_t x_addr = w_addr + kTWBytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(w_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc(x_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+          if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: lane = output channel
+    // TMEM row = channel, columns = pixels.  Eight warps: warp (quad, half) owns TMEM lanes
+    // 32*quad.. and the 32-pixel chunks c with c % 2 == half.  Per chunk: bias / activation / bf16
+    // rounding and BN sums on the thread's own channel, then a transpose through shared memory (lane
+    // pairs swap one value per pixel pair so that every thread writes a packed {co, co+1} word) and
+    // 16-byte NHWC stores.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int co = quad * 32 + lane;
+    const EpiParams& e = p.e;
+    const float slope = resolve_slope(e);
+    const bool warp_active = quad * 32 < p.cout;
+    const float bias = (warp_active && e.bias) ? e.bias[co] : 0.f;
+    const int hw = p.GH * p.GW;
+    const int active = p.cout < 128 ? 64 : 128;          // threads per half that own real channels
+    const int tid_a = quad * 32 + lane;
+    const int row_words = p.cout / 2 + 16;                 // staging row pitch in 32-bit words
+    const int segs = p.cout / 8;                           // 16-byte segments per pixel
+    if (e.stats)
+      for (int i = threadIdx.x - 64; i < 2 * 128; i += 256) s_sum[i] = 0.f;
+    float s1 = 0.f, s2 = 0.f;   // BN statistics of this channel over this warp's chunks
+    uint32_t it = 0, chunk_no = 0;
+    for (int tile = blockIdx.x; tile < p.p_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, use = it >> 1;
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
+      tc_fence_after();
+      if (warp_active) {
+        const int m0 = tile * kTP;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kTP;
+        uint32_t raw[32];
+        tmem_ld_32x32(trow + half * 32, raw);
+#pragma unroll 1
+        for (int c = half; c < kTP / 32; c += 2, ++chunk_no) {
+          uint32_t* stage = s_stage[half];
+          tmem_ld_wait();
+          const int px0 = m0 + c * 32;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(raw[i]) + bias;
+            if (e.act != ACT_NONE) x = x > 0.f ? x : x * slope;
+            x = bf16_round(x);
+            v[i] = x;
+            if (px0 + i < p.M) {
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+          }
+          if (c + 2 < kTP / 32) tmem_ld_32x32(trow + (c + 2) * 32, raw);   // prefetch the next chunk
+          const bool odd = lane & 1;
+          // the staging tile is free again once every thread finished the previous chunk's stores
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(active) : "memory");
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[i] : v[i + 1], 1);
+            const uint32_t word = odd ? pack_bf16x2(recv, v[i + 1]) : pack_bf16x2(v[i], recv);
+            stage[(i + (odd ? 1 : 0)) * row_words + (co >> 1)] = word;
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(active) : "memory");
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int idx = tid_a + k * active;
+            const int row = idx / segs, seg = idx - row * segs;
+            const int px = px0 + row;
+            if (px < p.M) {
+              size_t opix;
+              if (p.flat) {
+                opix = static_cast<size_t>(px);
+              } else {
+                const int n_img = px / hw;
+                const int rem = px - n_img * hw;
+                const int gh = rem / p.GW;
+                const int gw = rem - gh * p.GW;
+                opix = static_cast<size_t>(n_img * e.OH + gh * e.osy + e.opy) * e.OW + gw * e.osx + e.opx;
+              }
+              const uint4 val = *reinterpret_cast<const uint4*>(stage + row * row_words + seg * 4);
+              *reinterpret_cast<uint4*>(e.out + opix * e.ldc + seg * 8) = val;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+    }
+    if (e.stats) {
+      asm volatile("bar.sync 3, 256;" ::: "memory");      // s_sum zeroed by all epilogue threads
+      if (warp_active) {
+        atomicAdd(&s_sum[co], s1);
+        atomicAdd(&s_sum[128 + co], s2);
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      float* mine = e.stats + static_cast<size_t>(blockIdx.x) * 2 * p.cout;
+      for (int i = threadIdx.x - 64; i < 2 * p.cout; i += 256)
+        mine[i] = s_sum[(i < p.cout) ? i : 128 + (i - p.cout)];
+      for (int r = gridDim.x + blockIdx.x; r < e.stats_rows; r += gridDim.x) {
+        float* z = e.stats + static_cast<size_t>(r) * 2 * p.cout;
+        for (int i = threadIdx.x - 64; i < 2 * p.cout; i += 256) z[i] = 0.f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kTP);
+  }
+}
+
+// ------------------------------------------------------------------ halo-fed kernel
 template <int BN, int STAGES>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, int grid,
-                   cudaStream_t stream) {
-  const int smem_bytes = STAGES * SmemLayout<BN>::kStageBytes + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const HParams p) {
+  constexpr int kBTile = BN * kBK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_b = smem + 2 * kHaloABytes;
+  __shared__ __align__(8) uint64_t a_full[2];
+  __shared__ __align__(8) uint64_t a_empty[2];
+  __shared__ __align__(8) uint64_t b_full[STAGES];
+  __shared__ __align__(8) uint64_t b_empty[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_stats[2 * kMaxCout];
+  __shared__ float s_bias[kMaxCout];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int cout = p.n_tiles * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&a_full[i]), 1);
+      mbar_init(smem_u32(&a_empty[i]), 1);
+      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), 2 * BN);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < cout; i += 128) s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
+    if (p.e.stats)
+      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) s_stats[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      if (p.resident) {   // the whole [Cout, 9*64] weight matrix: nine B tiles, loaded once
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t fb = smem_u32(&b_full[tap]);
+          mbar_expect_tx(fb, kBTile);
+          tma_load_2d(smem_u32(smem_b + tap * kBTile), &tmap_b, fb, p.k_off[tap], 0);
+        }
+      }
+      uint32_t ub = 0, kbg = 0;   // A-box counter, B-stage counter (pipeline phases)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tile_m = tile / p.n_tiles;
+        const int n0 = (tile % p.n_tiles) * BN;
+        const int n_img = tile_m / p.tiles_hw;
+        const int r2 = tile_m - n_img * p.tiles_hw;
+        const int h0 = (r2 / p.tiles_w) * p.R;
+        const int w0 = (r2 % p.tiles_w) * p.TW;
+        for (int cb = 0; cb < p.cin_blocks; ++cb, ++ub) {
+          const uint32_t ab = ub & 1;
+          mbar_wait(smem_u32(&a_empty[ab]), ((ub >> 1) & 1) ^ 1);
+          const uint32_t fa = smem_u32(&a_full[ab]);
+          mbar_expect_tx(fa, p.a_bytes);
+          tma_load_4d(smem_u32(smem + ab * kHaloABytes), &tmap_a, fa, cb * kBK, w0 - 1, h0 - 1, n_img);
+          if (!p.resident) {
+            for (int tap = 0; tap < 9; ++tap, ++kbg) {
+              const uint32_t s = kbg % STAGES;
+              mbar_wait(smem_u32(&b_empty[s]), ((kbg / STAGES) & 1) ^ 1);
+              const uint32_t fb = smem_u32(&b_full[s]);
+              mbar_expect_tx(fb, kBTile);
+              tma_load_2d(smem_u32(smem_b + s * kBTile), &tmap_b, fb, p.k_off[tap] + cb * kBK, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    uint32_t ub = 0, kbg = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, use = it >> 1;
+      mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int cb = 0; cb < p.cin_blocks; ++cb, ++ub) {
+        const uint32_t ab = ub & 1;
+        mbar_wait(smem_u32(&a_full[ab]), (ub >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + ab * kHaloABytes);
+        for (int tap = 0; tap < 9; ++tap) {
+          uint32_t s, parity;
+          if (p.resident) {
+            s = tap;
+            parity = 0;
+          } else {
+            s = kbg % STAGES;
+            parity = (kbg / STAGES) & 1;
+          }
+          mbar_wait(smem_u32(&b_full[s]), parity);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_tap = a_addr + p.shift[tap] * 128;
+            const uint32_t b_addr = smem_u32(smem_b + s * kBTile);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t da = umma_smem_desc(a_tap + k * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16(tmem_d, da, db, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            if (!p.resident) umma_commit(smem_u32(&b_empty[s]));
+          }
+          __syncwarp();
+          if (!p.resident) ++kbg;
+        }
+        if (lane == 0) {
+          umma_commit(smem_u32(&a_empty[ab]));
+          if (cb == p.cin_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int quad = warp & 3;
+    const float slope = resolve_slope(p.e);
+    const int i = quad * 32 + lane;        // accumulator row = r * PW + c
+    const int r = i / p.PW, c = i - r * p.PW;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, use = it >> 1;
+      const int tile_m = tile / p.n_tiles;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int n_img = tile_m / p.tiles_hw;
+      const int r2 = tile_m - n_img * p.tiles_hw;
+      int gh = (r2 / p.tiles_w) * p.R + r;
+      int gw = (r2 % p.tiles_w) * p.TW + c;
+      const bool valid = c < p.TW && r < p.R && gh < p.H && gw < p.W;
+      if (!valid) gh = gw = 0;
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
+      tc_fence_after();
+      epilogue_tile<BN>(p.e, tmem_base + acc * BN, quad, lane, n0, cout, n_img, gh, gw, valid, slope,
+                        s_bias, s_stats);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+    }
+    if (p.e.stats) flush_stats(p.e, s_stats, cout);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+template <typename K, typename P>
+int launch_kernel(K kernel, bool* configured, int smem_bytes, const CUtensorMap& ta, const CUtensorMap& tb,
+                  const P& kp, int grid, cudaStream_t stream, int threads = kThreads) {
+  if (!*configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return 3;
     }
-    configured = true;
+    *configured = true;
   }
-  igemm_tc_kernel<BN, STAGES><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, kp);
+  kernel<<<grid, threads, smem_bytes, stream>>>(ta, tb, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "igemm launch: %s", cudaGetErrorString(e));
@@ -330,8 +734,24 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
   return 0;
 }
 
-bool g_force_im2col = true;    // tiled-mode A boxes measured no faster than im2col mode (same L2 traffic)
-                               // and their tile counts quantise worse; igemm_force_im2col(0) enables them
+template <int BN, int STAGES>
+int launch_im2col(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, int grid,
+                  cudaStream_t stream) {
+  static bool configured = false;
+  return launch_kernel(igemm_tc_kernel<BN, STAGES>, &configured, STAGES * SmemLayout<BN>::kStageBytes + 1024,
+                       ta, tb, kp, grid, stream);
+}
+template <int BN, int STAGES>
+int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const HParams& hp, int grid,
+                cudaStream_t stream) {
+  static bool configured = false;
+  return launch_kernel(igemm_halo_kernel<BN, STAGES>, &configured,
+                       2 * kHaloABytes + STAGES * BN * kBK * 2 + 1024, ta, tb, hp, grid, stream);
+}
+
+int g_halo_mode = 0;   // 0: never (default: measured slower, see header), 1: cost model, 2: whenever the
+                       // geometry allows (tests)
+int g_transposed = 1;  // 1: Cout <= 128 layers run with the pixels on the UMMA N side
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -344,32 +764,86 @@ int num_sms() {
   return g_num_sms;
 }
 
-// Tile width: minimise waves x (MMA cycles of one tile + per-tile bubble); ties go to the wider
-// tile, which re-reads the activation operand fewer times.
-int pick_bn(int m_tiles, int cout, int ps_c, int num_kb) {
+// Cost model (cycles): a tile costs max(operand bytes / L2->SM rate, MMA cycles) + a fixed bubble;
+// the persistent grid runs ceil(tiles / SMs) of them back to back.
+constexpr double kL2BytesPerClk = 48.0;
+constexpr double kTileBubble = 400.0;
+double plan_cost(long long tiles, double bytes_per_tile, double mma_clk) {
+  const long long waves = (tiles + num_sms() - 1) / num_sms();
+  const double t = bytes_per_tile / kL2BytesPerClk;
+  return static_cast<double>(waves) * ((t > mma_clk ? t : mma_clk) + kTileBubble);
+}
+
+struct Plan {
+  int halo, bn, tw, r, tiles_w, tiles_h, resident;
+  double cost;
+};
+
+Plan make_plan(const IgemmProblem& p) {
+  Plan best{};
+  best.cost = -1.0;
+  const long long M = static_cast<long long>(p.NB) * p.GH * p.GW;
+  const int m_tiles_i = static_cast<int>((M + kBM - 1) / kBM);
+  const int cin_blocks = p.Cin / kBK;
   const int cands[3] = {256, 128, 64};
-  long long best_cost = 0;
-  int best = 0;
+  // halo geometry
+  bool halo_ok = g_halo_mode > 0 && p.trav_stride == 1 && p.GH == p.H && p.GW == p.W && p.num_taps == 9 &&
+                 p.lower_w == -1 && p.lower_h == -1;
+  for (int t = 0; halo_ok && t < 9; ++t) halo_ok = p.taps.off_w[t] <= 2 && p.taps.off_h[t] <= 2;
+  int tw = 0, r = 0, tiles_w = 0, tiles_h = 0;
+  if (halo_ok) {
+    long long best_tiles = 0;
+    for (int cw = 4; cw <= 61 && cw <= p.W; ++cw) {
+      int rr = (128 - cw) / (cw + 2) + 1;
+      if (rr > p.H) rr = p.H;
+      if ((cw + 2) * (rr + 2) * 128 > kHaloABytes) continue;
+      const int nw = (p.W + cw - 1) / cw, nh = (p.H + rr - 1) / rr;
+      const long long nt = static_cast<long long>(nw) * nh;
+      if (tw == 0 || nt < best_tiles || (nt == best_tiles && cw > tw)) {
+        tw = cw; r = rr; tiles_w = nw; tiles_h = nh; best_tiles = nt;
+      }
+    }
+    if (tw == 0) halo_ok = false;
+  }
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
-    if (cout % bn) continue;
-    if (ps_c > 0 && (ps_c % 32)) continue;
-    const long long tiles = static_cast<long long>(m_tiles) * (cout / bn);
-    const long long waves = (tiles + num_sms() - 1) / num_sms();
-    const long long cost = waves * (2LL * bn * num_kb + 300);
-    if (best == 0 || cost < best_cost) {
-      best = bn;
-      best_cost = cost;
+    if (p.Cout % bn) continue;
+    if (p.ps_c > 0 && (p.ps_c % 32)) continue;
+    const int n_tiles = p.Cout / bn;
+    const double mma = 2.0 * bn * 9 * cin_blocks;
+    {
+      const double bytes = 9.0 * cin_blocks * (kATileBytes + bn * 128.0);
+      const double c = plan_cost(static_cast<long long>(m_tiles_i) * n_tiles, bytes, mma);
+      if (best.cost < 0 || c < best.cost) best = Plan{0, bn, 0, 0, 0, 0, 0, c};
+    }
+    if (halo_ok) {
+      const int stages = bn == 256 ? 4 : 9;
+      const int resident = (cin_blocks == 1 && n_tiles == 1 && stages >= 9) ? 1 : 0;
+      const double a_bytes = (tw + 2) * (r + 2) * 128.0;
+      const double bytes = cin_blocks * (a_bytes + (resident ? 0.0 : 9.0 * bn * 128.0));
+      double c = plan_cost(static_cast<long long>(p.NB) * tiles_h * tiles_w * n_tiles, bytes, mma);
+      if (g_halo_mode == 2) c = 0.0;
+      if (best.cost < 0 || c < best.cost) best = Plan{1, bn, tw, r, tiles_w, tiles_h, resident, c};
     }
   }
   return best;
+}
+
+void fill_epi(EpiParams& e, const IgemmProblem& p) {
+  e.out = p.out;
+  e.OH = p.OH; e.OW = p.OW; e.ldc = p.ldc;
+  e.osy = p.osy; e.osx = p.osx; e.opy = p.opy; e.opx = p.opx;
+  e.ps_c = p.ps_c;
+  e.bias = p.bias; e.act = p.act; e.slope = p.slope; e.slope_ptr = p.slope_ptr;
+  e.stats = p.stats; e.stats_rows = p.stats_rows;
 }
 
 }  // namespace
 
 const char* igemm_last_error() { return g_err; }
 int igemm_max_ctas() { return num_sms(); }
-void igemm_force_im2col(int on) { g_force_im2col = on != 0; }
+void igemm_set_halo_mode(int mode) { g_halo_mode = mode; }
+void igemm_set_transposed(int on) { g_transposed = on; }
 
 bool igemm_supported(const IgemmProblem& p) {
   if (p.Cin % 64 || p.Cout % 64 || p.Cout > kMaxCout) return false;
@@ -389,42 +863,82 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
              p.Cout, p.num_taps, p.ldc);
     return 1;
   }
-  const long long M = static_cast<long long>(p.NB) * p.GH * p.GW;
-  int m_tiles = static_cast<int>((M + kBM - 1) / kBM);
-  // rectangular M tiles + tiled-mode TMA when a rectangle covers the image with >= 85 % useful rows
-  int tw = 0, th = 0, tiles_w = 0, tiles_h = 0;
-  if (p.trav_stride == 1 && p.GH == p.H && p.GW == p.W && !g_force_im2col) {
-    const int cand_w[7] = {p.W <= 128 ? p.W : 0, 128, 64, 32, 16, 8, 4};
-    double best = 0.0;
-    for (int i = 0; i < 7; ++i) {
-      const int cw = cand_w[i];
-      if (cw <= 0 || cw > p.W) continue;
-      const int chh = 128 / cw;
-      const int nw = (p.W + cw - 1) / cw, nh = (p.H + chh - 1) / chh;
-      const double eff = static_cast<double>(p.H) * p.W / (static_cast<double>(nw) * nh * 128.0);
-      if (eff > best + 1e-9) {
-        best = eff; tw = cw; th = chh; tiles_w = nw; tiles_h = nh;
-      }
+  const bool flat_out = p.osy == 1 && p.osx == 1 && p.opy == 0 && p.opx == 0 && p.OH == p.GH && p.OW == p.GW;
+  if (g_transposed && p.Cout <= 128 && p.ps_c == 0 && flat_out && g_halo_mode != 2) {
+    CUtensorMap tpx, tw;
+    if (make_tmap_2d_bf16(&tw, p.w, p.Cout, p.Ktot, p.Ktot, kBK, 128)) {
+      snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
+      return 2;
     }
-    if (best < 0.85) tw = 0;
+    if (make_tmap_im2col_nhwc_bf16(&tpx, p.x, p.NB, p.H, p.W, p.Cin, p.lower_w, p.lower_h, p.upper_w,
+                                   p.upper_h, kBK, kTP, p.trav_stride)) {
+      snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
+      return 2;
+    }
+    const long long Mt = static_cast<long long>(p.NB) * p.GH * p.GW;
+    TParams tp;
+    tp.M = static_cast<int>(Mt);
+    tp.GH = p.GH; tp.GW = p.GW; tp.trav_stride = p.trav_stride;
+    tp.lower_w = p.lower_w; tp.lower_h = p.lower_h;
+    tp.cin_blocks = p.Cin / kBK;
+    tp.num_taps = p.num_taps;
+    tp.p_tiles = static_cast<int>((Mt + kTP - 1) / kTP);
+    tp.cout = p.Cout;
+    tp.taps = p.taps;
+    fill_epi(tp.e, p);
+    tp.flat = (p.osy == 1 && p.osx == 1 && p.opy == 0 && p.opx == 0 && p.OH == p.GH && p.OW == p.GW) ? 1 : 0;
+    const int grid = tp.p_tiles < num_sms() ? tp.p_tiles : num_sms();
+    static bool configured = false;
+    return launch_kernel(igemm_t_kernel<4>, &configured, 4 * kTStage + 1024, tpx, tw, tp, grid, stream,
+                         kTThreads);
   }
-  if (tw) m_tiles = p.NB * tiles_h * tiles_w;
-  const int bn = pick_bn(m_tiles, p.Cout, p.ps_c, p.num_taps * (p.Cin / kBK));
-  if (!bn) {
+  const Plan pl = make_plan(p);
+  if (pl.cost < 0) {
     snprintf(g_err, sizeof g_err, "igemm: no tile for Cout=%d", p.Cout);
     return 1;
   }
+  const int bn = pl.bn;
   CUtensorMap ta, tb;
-  if (tw ? make_tmap_tiled_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, kBK, tw, th)
-         : make_tmap_im2col_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, p.lower_w, p.lower_h, p.upper_w,
-                                      p.upper_h, kBK, kBM, p.trav_stride)) {
-    snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
-    return 2;
-  }
   if (make_tmap_2d_bf16(&tb, p.w, p.Cout, p.Ktot, p.Ktot, kBK, bn)) {
     snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
     return 2;
   }
+  if (pl.halo) {
+    if (make_tmap_tiled_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, kBK, pl.tw + 2, pl.r + 2)) {
+      snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
+      return 2;
+    }
+    HParams hp;
+    hp.H = p.H; hp.W = p.W;
+    hp.TW = pl.tw; hp.R = pl.r; hp.PW = pl.tw + 2;
+    hp.tiles_w = pl.tiles_w; hp.tiles_hw = pl.tiles_w * pl.tiles_h;
+    hp.m_tiles = p.NB * hp.tiles_hw;
+    hp.n_tiles = p.Cout / bn;
+    hp.cin_blocks = p.Cin / kBK;
+    hp.a_bytes = hp.PW * (pl.r + 2) * 128;
+    hp.resident = pl.resident;
+    for (int t = 0; t < 9; ++t) {
+      hp.shift[t] = p.taps.off_h[t] * hp.PW + p.taps.off_w[t];
+      hp.k_off[t] = p.taps.k_off[t];
+    }
+    fill_epi(hp.e, p);
+    const int tiles = hp.m_tiles * hp.n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    switch (bn) {
+      case 64:
+        return launch_halo<64, 9>(ta, tb, hp, grid, stream);
+      case 128:
+        return launch_halo<128, 9>(ta, tb, hp, grid, stream);
+      default:
+        return launch_halo<256, 4>(ta, tb, hp, grid, stream);
+    }
+  }
+  if (make_tmap_im2col_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, p.lower_w, p.lower_h, p.upper_w,
+                                 p.upper_h, kBK, kBM, p.trav_stride)) {
+    snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
+    return 2;
+  }
+  const long long M = static_cast<long long>(p.NB) * p.GH * p.GW;
   KParams kp;
   kp.M = static_cast<int>(M);
   kp.GH = p.GH;
@@ -435,35 +949,18 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.cin_blocks = p.Cin / kBK;
   kp.num_taps = p.num_taps;
   kp.n_tiles = p.Cout / bn;
-  kp.m_tiles = m_tiles;
-  kp.tiled = tw ? 1 : 0;
-  kp.TW = tw; kp.TH = th; kp.tiles_w = tiles_w; kp.tiles_hw = tiles_w * tiles_h;
-  kp.a_bytes = tw ? tw * th * kBK * 2 : kATileBytes;
+  kp.m_tiles = static_cast<int>((M + kBM - 1) / kBM);
   kp.taps = p.taps;
-  kp.out = p.out;
-  kp.OH = p.OH;
-  kp.OW = p.OW;
-  kp.ldc = p.ldc;
-  kp.osy = p.osy;
-  kp.osx = p.osx;
-  kp.opy = p.opy;
-  kp.opx = p.opx;
-  kp.ps_c = p.ps_c;
-  kp.bias = p.bias;
-  kp.act = p.act;
-  kp.slope = p.slope;
-  kp.slope_ptr = p.slope_ptr;
-  kp.stats = p.stats;
-  kp.stats_rows = p.stats_rows;
-  const int tiles = m_tiles * kp.n_tiles;
+  fill_epi(kp.e, p);
+  const int tiles = kp.m_tiles * kp.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   switch (bn) {
     case 64:
-      return launch_variant<64, 8>(ta, tb, kp, grid, stream);
+      return launch_im2col<64, 8>(ta, tb, kp, grid, stream);
     case 128:
-      return launch_variant<128, 6>(ta, tb, kp, grid, stream);
+      return launch_im2col<128, 6>(ta, tb, kp, grid, stream);
     default:
-      return launch_variant<256, 4>(ta, tb, kp, grid, stream);
+      return launch_im2col<256, 4>(ta, tb, kp, grid, stream);
   }
 }
 

@@ -85,8 +85,10 @@ def run(kind, name, h, cin, cout, stride, ps, stats):
 
 
 def main():
-    if os.environ.get("FORCE_IM2COL"):
-        _lib.query("sisr_debug_force_im2col", 1)
+    if os.environ.get("HALO_MODE"):
+        _lib.query("sisr_debug_halo_mode", int(os.environ["HALO_MODE"]))
+    if os.environ.get("TRANSPOSED"):
+        _lib.query("sisr_debug_transposed", int(os.environ["TRANSPOSED"]))
     kinds = ["fprop", "dgrad", "wgrad"] if len(sys.argv) < 2 or sys.argv[1] == "all" else [sys.argv[1]]
     filt = sys.argv[2] if len(sys.argv) > 2 else ""
     tot = {k: 0.0 for k in kinds}
