@@ -10,8 +10,9 @@ torchrun, one rank per GPU): same per-GPU batch (weak scaling), NCCL gradient al
 One JSON line on stdout (rank 0).  ``value`` = patches/s with the batch resident in HBM (whole step
 replayed as one CUDA graph at N = 1); ``e2e`` = the same step fed from pinned HOST buffers with the
 H2D copy of HR+LR and a D2H read of the three losses inside the timed region; ``roofline`` = the
-dominant kernel (tcgen05 implicit-GEMM conv) timed alone with CUDA events against the measured bf16
-peak; ``cpu_baseline`` = the CPU oracle port of the reference step on the box's host cores.
+dominant kernel (tcgen05 implicit-GEMM conv) timed alone (CUDA graph of back-to-back launches, CUDA
+events) against the measured bf16 peak; ``roofline_hbm`` = the fused BN / PReLU kernels against the
+measured HBM bandwidth; ``cpu_baseline`` = the CPU oracle port of the reference step on the box's host cores.
 ``--impl reference`` times the reference's own CPU implementation of the step (the oracle port:
 /root/reference does not exist on the GPU box) with all host threads on a bounded sample.
 """
@@ -148,41 +149,92 @@ def build_trainer(dev, batch, world, grad_sync=None):
     return tr
 
 
-def time_conv_kernel(dev, n, h, cin, cout, with_stats, iters=20):
-    """CUDA-event timing of one tcgen05 implicit-GEMM conv launch through the C ABI, L2 flushed
-    (a 256 MB write) before every launch."""
+def _graph_time_us(launch, reps=12, replays=5):
+    """Device time per launch: `reps` launches captured in one CUDA graph (no host gaps; the tensor maps
+    are encoded at capture), timed with CUDA events on the replaying stream."""
+    import torch
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for i in range(3):
+            launch(i, side.cuda_stream)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        st = torch.cuda.current_stream().cuda_stream
+        for i in range(reps):
+            launch(i, st)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * replays)
+
+
+def time_conv_kernel(dev, n, h, cin, cout, with_stats):
+    """One tcgen05 conv launch through the C ABI, timed inside a CUDA graph of back-to-back launches that
+    rotate over 3 input / output sets (the trunk tensors are L2-resident in the real step as well)."""
     import torch
     from sisr_b200 import _lib
-    w = h
-    x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
-    wt = (torch.randn(cout, 3, 3, cin, device=dev) * 0.02).to(torch.bfloat16)
+    sets = []
+    for _ in range(3):
+        x = torch.randn(n, h, h, cin, device=dev).to(torch.bfloat16)
+        wt = (torch.randn(cout, 3, 3, cin, device=dev) * 0.02).to(torch.bfloat16)
+        y = torch.empty(n, h, h, cout, device=dev, dtype=torch.bfloat16)
+        stats = torch.empty(_lib.query("sisr_stats_rows"), 2 * cout, device=dev) if with_stats else None
+        sets.append((x, wt, y, stats))
     bias = torch.zeros(cout, device=dev)
-    y = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
-    stats = torch.empty(2 * cout, device=dev) if with_stats else None
-    d = _lib.ConvDesc(n, h, w, cin, h, w, cout, 3, 1, 1, 0)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
-    ms = []
-    for i in range(iters + 3):
-        flush.zero_()                                  # evict L2 (126 MB) between launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    d = _lib.ConvDesc(n, h, h, cin, h, h, cout, 3, 1, 1, 0)
+
+    def launch(i, st):
+        x, wt, y, stats = sets[i % 3]
         _lib.call("sisr_conv_fprop", d, x, wt, bias, 0, 0.0, None, y, None, stats, st)
-        e1.record()
-        e1.synchronize()
-        if i >= 3:
-            ms.append(e0.elapsed_time(e1))
-    flops = 2.0 * n * h * w * cout * 9 * cin
-    avg = sum(ms) / len(ms)
-    return {"kernel": "igemm_tc_kernel conv3x3 %d->%d @%dx%d batch %d%s" %
-                      (cin, cout, h, w, n, " +BN stats" if with_stats else ""),
-            "flops": flops, "ms": avg, "tflops": flops / (avg * 1e-3) / 1e12}
+    us = _graph_time_us(launch)
+    flops = 2.0 * n * h * h * cout * 9 * cin
+    return {"kernel": "conv3x3 %d->%d @%dx%d batch %d%s" % (cin, cout, h, h, n, " +BN stats" if with_stats else ""),
+            "flops": flops, "ms": us * 1e-3, "tflops": flops / (us * 1e-6) / 1e12}
 
 
 def time_dominant_kernel(dev, batch):
-    """The kernel with the largest share of the step (profiles/: igemm_tc_kernel<64,4>, 18 %) on its
-    most frequent shape: the generator trunk conv 64->64 @24x24 with fused BN statistics."""
+    """igemm_t_kernel (17.7 % of the step, profiles/r1_step_launches_b64_t33.csv) on its most frequent
+    shape: the generator trunk conv 64->64 @24x24 with fused BN statistics (33 of its 93 launches)."""
     return time_conv_kernel(dev, batch, 24, 64, 64, True)
+
+
+def time_hbm_kernels(dev, batch):
+    """Achieved algorithmic GB/s of the fused BN / PReLU kernels on the largest activation of the step
+    (generator up-scale output, batch x 96 x 96 x 64 bf16 = 75 MB per tensor)."""
+    import torch
+    from sisr_b200 import _lib
+    rows, c = batch * 96 * 96, 64
+    sets = [(torch.randn(rows, c, device=dev).to(torch.bfloat16), torch.randn(rows, c, device=dev).to(torch.bfloat16),
+             torch.empty(rows, c, device=dev, dtype=torch.bfloat16)) for _ in range(3)]
+    scale, shift = torch.rand(c, device=dev) + 0.5, torch.randn(c, device=dev)
+    mean, invstd = torch.randn(c, device=dev) * 0.1, torch.rand(c, device=dev) + 0.5
+    slope = torch.full((1,), 0.25, device=dev)
+    sums, colsum = torch.zeros(2 * c + 1, device=dev), torch.zeros(c, device=dev)
+    nb = rows * c * 2
+    cases = [
+        ("bn_apply+PReLU", 2 * nb, lambda i, s: _lib.call("sisr_bn_apply", sets[i % 3][0], scale, shift, 3, 0.0, slope,
+                                                           None, sets[i % 3][2], rows, c, s)),
+        ("bn_apply+residual", 3 * nb, lambda i, s: _lib.call("sisr_bn_apply", sets[i % 3][0], scale, shift, 0, 0.0, None,
+                                                              sets[i % 3][1], sets[i % 3][2], rows, c, s)),
+        ("bn_bwd_reduce", 2 * nb, lambda i, s: _lib.call("sisr_bn_bwd_reduce", sets[i % 3][1], sets[i % 3][0], mean, invstd,
+                                                          scale, shift, 3, 0.0, slope, sums, rows, c, s)),
+        ("bn_bwd_apply", 3 * nb, lambda i, s: _lib.call("sisr_bn_bwd_apply", sets[i % 3][1], sets[i % 3][0], mean, invstd,
+                                                         scale, shift, 3, 0.0, slope, sums, float(rows), sets[i % 3][2],
+                                                         colsum, rows, c, s)),
+        ("act_bwd(PReLU)", 3 * nb, lambda i, s: _lib.call("sisr_act_bwd", sets[i % 3][1], sets[i % 3][0], 3, 0.0, slope,
+                                                           sets[i % 3][2], None, colsum, rows, c, s)),
+    ]
+    out = []
+    for name, nbytes, fn in cases:
+        us = _graph_time_us(fn, reps=6, replays=3)
+        out.append({"kernel": name, "bytes": nbytes, "us": us, "GBps": nbytes / (us * 1e-6) / 1e9})
+    return out
 
 
 def run_ours(args):
@@ -281,8 +333,9 @@ def run_ours(args):
         return
     peaks = measured_peaks()
     dom = time_dominant_kernel(dev, batch)
-    others = [time_conv_kernel(dev, batch, 24, 256, 256, False), time_conv_kernel(dev, batch, 48, 128, 128, False),
-              time_conv_kernel(dev, batch, 12, 512, 512, False)]
+    others = [time_conv_kernel(dev, batch, 96, 64, 64, False), time_conv_kernel(dev, batch, 48, 128, 128, False),
+              time_conv_kernel(dev, batch, 24, 256, 256, False), time_conv_kernel(dev, batch, 12, 512, 512, False)]
+    hbm = time_hbm_kernels(dev, batch)
     total_patches = batch * world * args.steps
     value = total_patches / (ms * 1e-3)
     line = {
@@ -307,12 +360,21 @@ def run_ours(args):
                 "d2h_bytes_per_step": 12},
         "gpu_launches": (launches_per_step or 0) * args.steps,
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_burst"],
-                     "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["bf16_burst"], "traffic": None,
-                     "kernel": dom["kernel"], "ms_per_launch": dom["ms"], "peak_source": peaks["source"],
-                     "share_of_step": "igemm_tc_kernel<64,4> = 18 % of step time (profiles/r1_step_launches_b64_eager.csv)",
-                     "l2_flushed_between_launches": True},
+                     "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["bf16_burst"],
+                     # dram__bytes_read + write of one launch, ncu --set full (profiles/r1_ncu_trunk_conv.txt):
+                     # 4.83 MB read (the input activation, cold), 0 written back (the output stays in L2)
+                     "traffic": 4831488,
+                     "kernel": "igemm_t_kernel: " + dom["kernel"], "ms_per_launch": dom["ms"],
+                     "peak_source": peaks["source"] + " (burst: kernel timed alone)",
+                     "share_of_step": "igemm_t_kernel = 17.7 % of the step's kernel time "
+                                      "(profiles/r1_step_launches_b64_t33.csv)",
+                     "timing": "12 back-to-back launches per CUDA graph over 3 rotating buffer sets (tensors "
+                               "L2-resident as in the step), CUDA events on the replaying stream"},
         "roofline_other": [{"kernel": o["kernel"], "achieved": o["tflops"], "unit": "TFLOP/s",
                             "frac": o["tflops"] / peaks["bf16_burst"], "ms_per_launch": o["ms"]} for o in others],
+        "roofline_hbm": [{"kernel": h["kernel"] + " on batch x 96x96x64 bf16", "bound": "hbm",
+                          "achieved": h["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
+                          "frac": h["GBps"] / peaks["hbm"], "us_per_launch": h["us"]} for h in hbm],
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
