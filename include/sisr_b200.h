@@ -202,6 +202,13 @@ int sisr_bn_finalize_sync(void* const* bases, int rank, int world, int slot, con
                           float momentum, float eps, float* scale, float* shift, float* mean,
                           float* invstd, int c, void* stream);
 
+/* sisr_bn_bwd_reduce with the cross-GPU exchange fused in: sums (caller zeroes) receives the LOCAL
+ * [2c+1] sums, sums_global the sums over all ranks; ticket: one zeroed 32-bit word of scratch */
+int sisr_bn_bwd_reduce_sync(void* const* bases, int rank, int world, int slot, const sisr_bf16* dout,
+                            const sisr_bf16* y, const float* mean, const float* invstd, const float* scale,
+                            const float* shift, int act, float slope, const float* slope_ptr, float* sums,
+                            float* sums_global, void* ticket, long long rows, int c, void* stream);
+
 /* ---- optimiser: torch.optim.Adam + LambdaLR (config.py:170-180, 293-294; train.py:75,108,121-122) ---- */
 int sisr_adam_tick(int* step, float lr0, float decay, float b1, float b2, float* hyper, void* stream);
 /* p/g/m/v/numel are HOST arrays of n device pointers / element counts */

@@ -478,6 +478,20 @@ int sisr_bn_finalize_sync(void* const* bases, int rank, int world, int slot, con
               "bn_finalize_sync");
 }
 
+/* sisr_bn_bwd_reduce + the cross-GPU exchange of its [2c+1] sums in one launch: the last CTA to finish
+ * runs the NVLink peer exchange and writes the global sums to sums_global. */
+int sisr_bn_bwd_reduce_sync(void* const* bases, int rank, int world, int slot, const sisr_bf16* dout,
+                            const sisr_bf16* y, const float* mean, const float* invstd, const float* scale,
+                            const float* shift, int act, float slope, const float* slope_ptr, float* sums,
+                            float* sums_global, void* ticket, long long rows, int c, void* s) {
+  if (!bases || world > kPeerMaxWorld || !sums_global || !ticket)
+    return fail(1, "bn_bwd_reduce_sync: bad arguments");
+  const PeerTable t = make_table(bases, rank, world);
+  return wrap(bn_bwd_reduce(B(dout), B(y), mean, invstd, scale, shift, act, slope, slope_ptr, sums, rows, c,
+                            S(s), &t, slot, sums_global, static_cast<unsigned int*>(ticket)),
+              "bn_bwd_reduce_sync");
+}
+
 // ------------------------------------------------------------------ optimiser
 int sisr_adam_tick(int* step, float lr0, float decay, float b1, float b2, float* hyper, void* s) {
   return wrap(adam_tick(step, lr0, decay, b1, b2, hyper, S(s)), "adam_tick");

@@ -6,6 +6,7 @@
 
 #include <stdio.h>
 
+#include "peer_device.cuh"
 #include "ptx.cuh"
 
 namespace sisr {
@@ -308,7 +309,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
                      const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ scale, const float* __restrict__ shift, int act,
                      float slope, const float* __restrict__ slope_ptr, float* __restrict__ sums,
-                     long long M, int C) {
+                     long long M, int C, const __grid_constant__ PeerTable peer, int slot,
+                     float* __restrict__ sums_global, unsigned int* __restrict__ ticket) {
   __shared__ __align__(16) float s_red[2 * kRedFloats];
   __shared__ float s_sa[kThreads / 32];
   const float sl = resolve_slope(act, slope, slope_ptr);
@@ -363,6 +365,23 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
       float t = 0.f;
       for (int i = 0; i < kThreads / 32; ++i) t += s_sa[i];
       atomicAdd(&sums[2 * C], t);
+    }
+  }
+  // SyncBN (world > 1): the last CTA to finish exchanges the [2C+1] local sums with the peers over
+  // NVLink and writes the global sums (no separate all-reduce launch)
+  if (peer.world > 1) {
+    __shared__ unsigned int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      float* vals = s_red;                          // 2C+1 <= 2 * kRedFloats
+      const int n = 2 * C + 1;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) vals[i] = __ldcg(sums + i);
+      __syncthreads();
+      exchange(peer, slot, vals, n);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) sums_global[i] = vals[i];
     }
   }
 }
@@ -669,11 +688,16 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, int
 }
 int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float* mean,
                   const float* invstd, const float* scale, const float* shift, int act, float slope,
-                  const float* slope_ptr, float* sums, long long M, int C, cudaStream_t s) {
+                  const float* slope_ptr, float* sums, long long M, int C, cudaStream_t s,
+                  const PeerTable* peer, int slot, float* sums_global, unsigned int* ticket) {
   if (C % 8 || C / 8 > kThreads) return 1;
   const int rpb = kThreads / (C / 8);
+  PeerTable none{};
+  none.world = 1;
+  if (peer && peer->world > 1 && (!sums_global || !ticket || 2 * C + 1 > kPeerSlotFloats)) return 1;
   bn_bwd_reduce_kernel<<<grid_for(M, rpb * 4, 148 * 2), kThreads, 0, s>>>(
-      dout, y, mean, invstd, scale, shift, act, slope, slope_ptr, sums, M, C);
+      dout, y, mean, invstd, scale, shift, act, slope, slope_ptr, sums, M, C, peer ? *peer : none, slot,
+      sums_global, ticket);
   return check();
 }
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float* mean,

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "igemm.h"
+#include "peer.h"
 
 namespace sisr {
 
@@ -24,7 +25,9 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, int
              int C, cudaStream_t s);
 int bn_bwd_reduce(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float* mean,
                   const float* invstd, const float* scale, const float* shift, int act, float slope,
-                  const float* slope_ptr, float* sums, long long M, int C, cudaStream_t s);
+                  const float* slope_ptr, float* sums, long long M, int C, cudaStream_t s,
+                  const struct PeerTable* peer = nullptr, int slot = 0, float* sums_global = nullptr,
+                  unsigned int* ticket = nullptr);
 int bn_bwd_apply(const __nv_bfloat16* dout, const __nv_bfloat16* y, const float* mean,
                  const float* invstd, const float* scale, const float* shift, int act, float slope,
                  const float* slope_ptr, const float* sums, float count, __nv_bfloat16* dy,

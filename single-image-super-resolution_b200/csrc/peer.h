@@ -12,8 +12,8 @@ constexpr int kPeerSlotFloats = 1152;    // >= 2*512 + 1 values per exchange
 
 // Layout of every rank's workspace (identical on all ranks, allocated with cudaMalloc and mapped
 // into the peers through CUDA IPC):
-//   data  [kPeerSlots][kPeerMaxWorld][kPeerSlotFloats] fp32   row r of a slot is written by rank r
-//   flags [kPeerSlots][kPeerMaxWorld] u32                     epoch of the last write of rank r
+//   data  [kPeerSlots][kPeerMaxWorld][kPeerSlotFloats] {fp32 value, u32 epoch}   row r of a slot is
+//         written by rank r, 8 bytes per element in one store
 //   epoch [kPeerSlots] u32                                    local call counter of the slot
 size_t peer_workspace_bytes();
 

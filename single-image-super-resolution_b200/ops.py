@@ -419,23 +419,24 @@ class BnActFn(torch.autograd.Function):
         rows = y.numel() // c
         st = _stream()
         gout = gout.contiguous()
-        zbuf = torch.zeros(3 * c + 1, dtype=torch.float32, device=dev)
+        zbuf = torch.zeros(3 * c + 2, dtype=torch.float32, device=dev)
         sums = zbuf[:2 * c + 1]
-        colsum = zbuf[2 * c + 1:] if not ctx.skip_params else None
-        call("sisr_bn_bwd_reduce", gout, y, aux[2], aux[3], aux[0], aux[1], cfg.act, cfg.leaky_slope,
-             slope, sums, rows, c, st)
+        colsum = zbuf[2 * c + 1:3 * c + 1] if not ctx.skip_params else None
         local = sums
-        if cfg.training:
-            if cfg.sync and _world() > 1:
-                sums = sums.clone()
-                if _peer is not None:
-                    call("sisr_peer_allreduce", _peer.bases, _peer.rank, _peer.world, _peer.next_slot(),
-                         sums, 2 * c + 1, st)
-                else:
-                    _all_reduce(sums)
-            red = sums
+        synced = cfg.training and cfg.sync and _world() > 1
+        if synced and _peer is not None:
+            # local sums + NVLink exchange in one launch (the last CTA to finish runs the exchange)
+            red = torch.empty(2 * c + 1, dtype=torch.float32, device=dev)
+            call("sisr_bn_bwd_reduce_sync", _peer.bases, _peer.rank, _peer.world, _peer.next_slot(), gout, y,
+                 aux[2], aux[3], aux[0], aux[1], cfg.act, cfg.leaky_slope, slope, sums, red, zbuf[3 * c + 1:],
+                 rows, c, st)
         else:
-            red = torch.zeros_like(sums)   # eval mode: statistics are constants
+            call("sisr_bn_bwd_reduce", gout, y, aux[2], aux[3], aux[0], aux[1], cfg.act, cfg.leaky_slope,
+                 slope, sums, rows, c, st)
+            if synced:
+                sums = sums.clone()
+                _all_reduce(sums)
+            red = sums if cfg.training else torch.zeros_like(sums)   # eval: statistics are constants
         dy = None
         if ctx.needs_input_grad[0]:
             dy = torch.empty_like(y)
