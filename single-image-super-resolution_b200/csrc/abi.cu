@@ -340,7 +340,7 @@ int sisr_conv_wgrad_fused(const sisr_conv_desc* d, const sisr_bf16* x, const sis
     if (int rc = sisr_conv_wgrad(d, x, dy, partials, need_bias ? dbias_tmp : nullptr, nullptr, s)) return rc;
   }
   const float* bsrc = dbias_in ? dbias_in : dbias_tmp;
-  if (full % 16 == 0 && d->cin % 4 == 0)
+  if (d->cin % 64 == 0 && d->k == 3)
     return wrap(weight_grad_reduce_finish(partials, splits, w_orig, u, v, sigma, dw, bsrc, dbias, d->cout,
                                           d->cin, d->k, d->k, d->ps_r, accumulate, dot, S(s)),
                 "weight_grad_reduce_finish");

@@ -6,6 +6,7 @@
 
 #include <cooperative_groups.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace sisr {
 
@@ -251,6 +252,9 @@ weight_prep_batched_kernel(const __grid_constant__ PrepTable tab) {
   }
 }
 
+// Variant for small layers (few (co, 64 ci) slabs, many splits - the generator trunk): one float4
+// column of the prepared layout per thread group keeps 576 CTAs busy; dw is written with a 9-float
+// stride, which is harmless on a 147 KB tensor.
 // Split-K reduce + spectral-norm gradient + layout change in ONE cooperative kernel:
 //   phase 1: G = sum_k partial_k (prepared layout [co'][tap][ci]); dw[co][ci][tap] (+)= G / sigma;
 //            dot += <G, W_orig>; bias gradient copied
@@ -259,7 +263,7 @@ weight_prep_batched_kernel(const __grid_constant__ PrepTable tab) {
 // Block = 16 float4 columns x 16 split lanes.  phases: 3 = both (cooperative launch), 1 / 2 = one
 // phase per ordinary launch.
 __global__ void __launch_bounds__(256)
-wgrad_reduce_finish_kernel(const float* __restrict__ partials, int splits, const float* __restrict__ w,
+wgrad_reduce_finish_small_kernel(const float* __restrict__ partials, int splits, const float* __restrict__ w,
                            const float* __restrict__ u, const float* __restrict__ v,
                            const float* __restrict__ sigma, float* __restrict__ dot,
                            float* __restrict__ dw, const float* __restrict__ dbias_perm,
@@ -317,6 +321,86 @@ wgrad_reduce_finish_kernel(const float* __restrict__ partials, int splits, const
       if (threadIdx.x == 0) {
         float t = 0.f;
         for (int k = 0; k < 16; ++k) t += s_dot[k];
+        atomicAdd(dot, t);
+      }
+    }
+  }
+  if (phases == 3) cooperative_groups::this_grid().sync();
+  if ((phases & 2) && sigma) {
+    const float coef = (*reinterpret_cast<volatile float*>(dot)) * inv * inv;
+    const int K = Cin * taps;
+    for (long long o = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; o < total;
+         o += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int co = static_cast<int>(o / K);
+      const int k = static_cast<int>(o - static_cast<long long>(co) * K);
+      dw[o] -= coef * u[co] * v[k];
+    }
+  }
+}
+
+// Split-K reduce + spectral-norm gradient + layout change in ONE cooperative kernel:
+//   phase 1: G = sum_k partial_k (prepared layout [co'][tap][ci]); dw[co][ci][tap] (+)= G / sigma;
+//            dot += <G, W_orig>; bias gradient copied
+//   grid sync
+//   phase 2: dw -= dot / sigma^2 * u v^T            (gradient through sigma, u and v constant)
+// Block = 16 float4 columns x 16 split lanes.  phases: 3 = both (cooperative launch), 1 / 2 = one
+// phase per ordinary launch.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_finish_kernel(const float* __restrict__ partials, int splits, const float* __restrict__ w,
+                           const float* __restrict__ u, const float* __restrict__ v,
+                           const float* __restrict__ sigma, float* __restrict__ dot,
+                           float* __restrict__ dw, const float* __restrict__ dbias_perm,
+                           float* __restrict__ dbias, int Cout, int Cin, int taps, int ps_r,
+                           int accumulate, int phases) {
+  __shared__ float s_tile[64 * 9];      // one (co, 64 ci) slab in master order [ci][tap]
+  __shared__ float s_dot[8];
+  const long long total = static_cast<long long>(Cout) * taps * Cin;
+  const long long total4 = total / 4;
+  const float inv = sigma ? 1.f / *sigma : 1.f;
+  if (phases & 1) {
+    // work item = (prepared row co', 64-channel chunk): its 9 x 64 values are contiguous in BOTH layouts
+    // ([tap][ci] in the partials, [ci][tap] in dw / w), so the layout change is a shared-memory transpose
+    // and every global access is coalesced.
+    // (used for the large layers, which have few splits: one thread per float4 column of the slab)
+    const int chunks = Cin / 64;
+    const int tap_t = threadIdx.x >> 4, x = threadIdx.x & 15;
+    float dacc = 0.f;
+    for (int item = blockIdx.x; item < Cout * chunks; item += gridDim.x) {
+      const int cop = item / chunks, cic = item - cop * chunks;
+      const int co = unpermute_row(cop, Cout, ps_r);
+      if (tap_t < taps) {
+        const long long i4 = ((static_cast<long long>(cop) * taps + tap_t) * Cin + cic * 64) / 4 + x;
+        const float4* p = reinterpret_cast<const float4*>(partials) + i4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int k = 0; k < splits; ++k) {
+          const float4 t = __ldg(p + static_cast<long long>(k) * total4);
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        s_tile[(4 * x + 0) * taps + tap_t] = acc.x;
+        s_tile[(4 * x + 1) * taps + tap_t] = acc.y;
+        s_tile[(4 * x + 2) * taps + tap_t] = acc.z;
+        s_tile[(4 * x + 3) * taps + tap_t] = acc.w;
+      }
+      __syncthreads();
+      const size_t base = (static_cast<size_t>(co) * Cin + cic * 64) * taps;
+      for (int i = threadIdx.x; i < 64 * taps; i += blockDim.x) {
+        const float g = s_tile[i];
+        if (sigma) dacc = fmaf(g, w[base + i], dacc);
+        dw[base + i] = accumulate ? dw[base + i] + g * inv : g * inv;
+      }
+      if (dbias && cic == 0 && threadIdx.x == 0)
+        dbias[co] = accumulate ? dbias[co] + dbias_perm[cop] : dbias_perm[cop];
+      __syncthreads();
+    }
+    if (sigma) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+      if ((threadIdx.x & 31) == 0) s_dot[threadIdx.x >> 5] = dacc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += s_dot[k];
         atomicAdd(dot, t);
       }
     }
@@ -418,9 +502,8 @@ int weight_grad_reduce_finish(const float* partials, int splits, const float* w,
                               const float* v, const float* sigma, float* dw, const float* dbias_perm,
                               float* dbias, int Cout, int Cin, int KH, int KW, int ps_r, int accumulate,
                               float* dot, cudaStream_t s) {
-  const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
-  if (total % 4 || Cin % 4) return 1;
   int taps = KH * KW;
+  if (Cin % 64 || taps > 9) return 1;
   if (sigma) cudaMemsetAsync(dot, 0, sizeof(float), s);
   static int max_coop_blocks = -1;   // co-resident blocks of the cooperative kernel (0: unsupported)
   if (max_coop_blocks < 0) {
@@ -429,15 +512,22 @@ int weight_grad_reduce_finish(const float* partials, int splits, const float* w,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wgrad_reduce_finish_kernel, 256, 0);
+    int per_sm2 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, wgrad_reduce_finish_small_kernel, 256, 0);
+    if (per_sm2 < per_sm) per_sm = per_sm2;
     max_coop_blocks = (coop && per_sm > 0 && sms > 0) ? sms * (per_sm < 4 ? per_sm : 4) : 0;
     cudaGetLastError();
   }
-  long long want = (total / 4 + 15) / 16;
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  const long long slabs = static_cast<long long>(Cout) * (Cin / 64);
+  static const int force_small = getenv("SISR_DIAG_FINISH_SMALL") ? 1 : 0;   // A-B timing
+  const bool small = slabs < 512 || force_small;      // trunk-sized layers: parallelism over coalescing
+  auto kernel = small ? wgrad_reduce_finish_small_kernel : wgrad_reduce_finish_kernel;
+  long long want = small ? (total / 4 + 15) / 16 : slabs;
   if (!sigma) {   // no gradient through sigma: phase 1 alone is complete
     const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
-    wgrad_reduce_finish_kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw,
-                                                     dbias_perm, dbias, Cout, Cin, taps, ps_r,
-                                                     accumulate, 1);
+    kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw, dbias_perm, dbias, Cout, Cin, taps,
+                                ps_r, accumulate, 1);
     return check();
   }
   if (max_coop_blocks > 0 && !g_no_coop) {
@@ -445,15 +535,15 @@ int weight_grad_reduce_finish(const float* partials, int splits, const float* w,
     int phases = 3;
     void* args[] = {&partials, &splits, &w, &u, &v, &sigma, &dot, &dw, &dbias_perm, &dbias,
                     &Cout, &Cin, &taps, &ps_r, &accumulate, &phases};
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(wgrad_reduce_finish_kernel),
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel),
                                                 dim3(grid), dim3(256), args, 0, s);
     return e == cudaSuccess ? 0 : 4;
   }
   const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
-  wgrad_reduce_finish_kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw, dbias_perm,
-                                                   dbias, Cout, Cin, taps, ps_r, accumulate, 1);
-  wgrad_reduce_finish_kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw, dbias_perm,
-                                                   dbias, Cout, Cin, taps, ps_r, accumulate, 2);
+  kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw, dbias_perm, dbias, Cout, Cin, taps, ps_r,
+                              accumulate, 1);
+  kernel<<<grid, 256, 0, s>>>(partials, splits, w, u, v, sigma, dot, dw, dbias_perm, dbias, Cout, Cin, taps, ps_r,
+                              accumulate, 2);
   return check();
 }
 

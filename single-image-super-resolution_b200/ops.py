@@ -79,11 +79,43 @@ def set_peer_exchange(px):
     _peer = px
 
 
-def begin_step():
-    """Called by the trainer at the start of every step (all ranks): resets per-step numbering."""
+class _ZeroArena:
+    """One zero-filled fp32 buffer per step for the many tiny accumulators (BN backward sums, bias /
+    slope gradients): a single memset at the start of the step instead of ~75 fill kernels.  Every
+    slice is handed out at most once between two ``reset`` calls; without a trainer calling
+    ``begin_step`` the arena is never armed and callers get ``torch.zeros``."""
+
+    FLOATS = 1 << 19
+
+    def __init__(self):
+        self.buf, self.off = None, 0
+
+    def reset(self, dev):
+        if self.buf is None or self.buf.device != dev:
+            self.buf = torch.zeros(self.FLOATS, dtype=torch.float32, device=dev)
+        else:
+            self.buf.zero_()
+        self.off = 0
+
+    def take(self, n, dev):
+        if self.buf is None or self.buf.device != dev or self.off + n > self.FLOATS:
+            return torch.zeros(n, dtype=torch.float32, device=dev)
+        out = self.buf[self.off:self.off + n]
+        self.off += _round_up(n, 4)
+        return out
+
+
+_arena = _ZeroArena()
+
+
+def begin_step(device=None):
+    """Called by the trainer at the start of every step (all ranks): resets per-step numbering and
+    re-zeroes the accumulator arena."""
     _colsum_cache.clear()
     if _peer is not None:
         _peer.reset()
+    if device is not None and torch.device(device).type == "cuda":
+        _arena.reset(torch.device(device))
 
 
 def _world():
@@ -327,7 +359,7 @@ class Conv2dFn(torch.autograd.Function):
             want_db = ctx.needs_input_grad[2] and not ctx.skip_params and cfg.ps_r != 2
             c_last = gy.shape[-1]
             if want_ds or want_db:
-                zbuf = torch.zeros(1 + c_last, dtype=torch.float32, device=dev)
+                zbuf = _arena.take(1 + c_last, dev)
                 dslope = zbuf[:1] if want_ds else None
                 colsum = zbuf[1:] if want_db else None
             call("sisr_act_bwd", gy, y, cfg.act, cfg.leaky_slope, slope, dpre, dslope, colsum,
@@ -419,7 +451,7 @@ class BnActFn(torch.autograd.Function):
         rows = y.numel() // c
         st = _stream()
         gout = gout.contiguous()
-        zbuf = torch.zeros(3 * c + 2, dtype=torch.float32, device=dev)
+        zbuf = _arena.take(3 * c + 2, dev)
         sums = zbuf[:2 * c + 1]
         colsum = zbuf[2 * c + 1:3 * c + 1] if not ctx.skip_params else None
         local = sums

@@ -81,7 +81,7 @@ class SRGANTrainer:
     def step(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=()):
         """img_hr: (B,3,H,H) fp32 in [-1,1]; img_lr: (B,3,H/s,H/s).  Returns device scalars."""
         c = self.cfg
-        ops.begin_step()
+        ops.begin_step(img_hr.device)
         fake = self.net_g(img_lr)
 
         self.net_d.zero_grad(set_to_none=True)
