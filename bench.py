@@ -313,9 +313,10 @@ def run_ours(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     losses = None
+    from sisr_b200 import lr_from_hr
     for _ in range(args.steps):
         hr.copy_(hr_host, non_blocking=True)
-        lr.copy_(lr_host, non_blocking=True)
+        lr.copy_(lr_from_hr(hr, (24, 24)))          # utils.lr_from_hr on the device, as train.py:46 does
         out = step()
         losses = torch.stack([out["err_d"].reshape(()), out["err_g_adv"].reshape(()),
                               out["err_g_cont"].reshape(())]).cpu()      # D2H + sync
@@ -356,7 +357,7 @@ def run_ours(args):
         "losses": [float(x) for x in losses],
         "clocks": clocks,
         "e2e": {"value": total_patches / (ms_e2e * 1e-3), "unit": "patches/s",
-                "h2d_bytes_per_step": (hr_host.numel() + lr_host.numel()) * 4,
+                "h2d_bytes_per_step": hr_host.numel() * 4,
                 "d2h_bytes_per_step": 12},
         "gpu_launches": (launches_per_step or 0) * args.steps,
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_burst"],

@@ -173,6 +173,13 @@ int sisr_dhead_backward(const sisr_bf16* x_flat, const float* w0, const float* w
                         float* dw2, float* db2, float* dx_flat, int batch, int fc_in, int fc_mid,
                         int need_wgrad, void* stream);
 
+/* ---- LR synthesis: utils.lr_from_hr (utils.py:16-31) = F.interpolate(bicubic, align_corners=True) +
+ *      clamp to [-1,1]; NCHW fp32.  The backward (content_loss_on_lr mode, train.py:95-97) passes the
+ *      gradient where the interpolated value stayed inside (-1, 1). ---- */
+int sisr_lr_from_hr(const float* hr, float* lr, int n, int c, int h, int w, int oh, int ow, void* stream);
+int sisr_lr_from_hr_bwd(const float* hr, const float* dlr, float* dhr, int n, int c, int h, int w, int oh,
+                        int ow, void* stream);
+
 /* ---- losses: nn.BCELoss (config.py:107; train.py:135,159,177), feature MSE (train.py:183-186) ---- */
 int sisr_bce_fwd(const float* p, int n, float target, float* loss, float* mean_p, void* stream);
 int sisr_bce_bwd(const float* p, int n, float target, const float* gout, float* dp, void* stream);

@@ -11,6 +11,7 @@ from .model_discriminator import Discriminator
 from .model_generator import Generator, GeneratorSuffix
 from .optim import Adam
 from .train import SRGANTrainer, StepConfig
+from .utils import lr_from_hr
 
 __all__ = ["Generator", "GeneratorSuffix", "Discriminator", "MaskedVGG", "identity", "Adam",
-           "SRGANTrainer", "StepConfig"]
+           "SRGANTrainer", "StepConfig", "lr_from_hr"]

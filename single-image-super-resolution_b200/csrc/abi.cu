@@ -413,6 +413,17 @@ int sisr_dhead_backward(const sisr_bf16* x_flat, const float* w0, const float* w
               "dhead_backward");
 }
 
+// ------------------------------------------------------------------ LR synthesis
+int sisr_lr_from_hr(const float* hr, float* lr, int n, int c, int h, int w, int oh, int ow, void* s) {
+  if (!hr || !lr) return fail(1, "lr_from_hr: null argument");
+  return wrap(lr_from_hr(hr, lr, nullptr, nullptr, n, c, h, w, oh, ow, S(s)), "lr_from_hr");
+}
+int sisr_lr_from_hr_bwd(const float* hr, const float* dlr, float* dhr, int n, int c, int h, int w, int oh,
+                        int ow, void* s) {
+  if (!hr || !dlr || !dhr) return fail(1, "lr_from_hr_bwd: null argument");
+  return wrap(lr_from_hr(hr, nullptr, dlr, dhr, n, c, h, w, oh, ow, S(s)), "lr_from_hr_bwd");
+}
+
 // ------------------------------------------------------------------ losses
 int sisr_bce_fwd(const float* p, int n, float target, float* loss, float* mean_p, void* s) {
   return wrap(bce_fwd(p, n, target, loss, mean_p, S(s)), "bce_fwd");

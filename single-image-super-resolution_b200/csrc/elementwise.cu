@@ -559,6 +559,76 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x,
   }
 }
 
+// ------------------------------------------------------------------ LR synthesis (utils.py:16-31)
+// F.interpolate(mode='bicubic', align_corners=True) (cubic convolution, A = -0.75, border-clamped
+// taps) followed by the clamp to [-1, 1]; NCHW fp32 in and out.
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+__device__ __forceinline__ void cubic_source(int dst, float scale, int in_size, int& idx, float& t) {
+  const float real = scale * static_cast<float>(dst);
+  int i = static_cast<int>(floorf(real));
+  if (i > in_size - 1) i = in_size - 1;
+  float lam = real - static_cast<float>(i);
+  lam = fminf(fmaxf(lam, 0.f), 1.f);
+  idx = i;
+  t = lam;
+}
+// mode 0: lr = clamp(interp(hr));  mode 1 (backward): dhr += W^T (dlr masked where the interpolated
+// value left [-1, 1])
+__global__ void lr_from_hr_kernel(const float* __restrict__ hr, float* __restrict__ lr,
+                                  const float* __restrict__ dlr, float* __restrict__ dhr, int NC, int H,
+                                  int W, int OH, int OW, float sh, float sw) {
+  const long long total = static_cast<long long>(NC) * OH * OW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % OW);
+    const int oy = static_cast<int>((i / OW) % OH);
+    const long long nc = i / (static_cast<long long>(OW) * OH);
+    int ix, iy;
+    float tx, ty, wx[4], wy[4];
+    cubic_source(ox, sw, W, ix, tx);
+    cubic_source(oy, sh, H, iy, ty);
+    cubic_coeffs(tx, wx);
+    cubic_coeffs(ty, wy);
+    const float* src = hr + nc * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), H - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), W - 1);
+        row += src[yy * W + xx] * wx[b];
+      }
+      acc += row * wy[a];
+    }
+    if (!dlr) {
+      lr[i] = fminf(fmaxf(acc, -1.f), 1.f);
+    } else {
+      const float g = (acc > -1.f && acc < 1.f) ? dlr[i] : 0.f;
+      if (g != 0.f) {
+        float* dst = dhr + nc * H * W;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int yy = min(max(iy - 1 + a, 0), H - 1);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int xx = min(max(ix - 1 + b, 0), W - 1);
+            atomicAdd(dst + yy * W + xx, g * wx[b] * wy[a]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ losses
 // loss += weight/n * sum (a-b)^2 ;  (fp32 inputs)
 __global__ void mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
@@ -731,6 +801,16 @@ int maxpool2_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16*
   if (C % 8 || H % 2 || W % 2) return 1;
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   maxpool2_bwd_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(x, dy, dx, N, H, W, C);
+  return check();
+}
+int lr_from_hr(const float* hr, float* lr, const float* dlr, float* dhr, int N, int C, int H, int W, int OH,
+               int OW, cudaStream_t s) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) return 1;
+  const float sh = OH > 1 ? static_cast<float>(H - 1) / static_cast<float>(OH - 1) : 0.f;
+  const float sw = OW > 1 ? static_cast<float>(W - 1) / static_cast<float>(OW - 1) : 0.f;
+  if (dlr) cudaMemsetAsync(dhr, 0, sizeof(float) * static_cast<size_t>(N) * C * H * W, s);
+  const long long total = static_cast<long long>(N) * C * OH * OW;
+  lr_from_hr_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(hr, lr, dlr, dhr, N * C, H, W, OH, OW, sh, sw);
   return check();
 }
 int mse_fwd(const float* a, const float* b, long long n, float coef, float* loss, cudaStream_t s) {

@@ -38,6 +38,9 @@ int act_bwd(const __nv_bfloat16* dout, const __nv_bfloat16* out, int act, float 
 int maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int N, int H, int W, int C, cudaStream_t s);
 int maxpool2_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16* dx, int N, int H,
                  int W, int C, cudaStream_t s);
+// lr = clamp(bicubic(hr)) (dlr == nullptr) or its backward dhr (dlr != nullptr)
+int lr_from_hr(const float* hr, float* lr, const float* dlr, float* dhr, int N, int C, int H, int W, int OH,
+               int OW, cudaStream_t s);
 int mse_fwd(const float* a, const float* b, long long n, float coef, float* loss, cudaStream_t s);
 int mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
             float* gb, cudaStream_t s);

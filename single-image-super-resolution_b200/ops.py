@@ -107,11 +107,58 @@ class _ZeroArena:
 
 _arena = _ZeroArena()
 
+# Weight gradients on a side stream (enabled by the trainer): the wgrad + finish kernels of a conv only
+# feed the optimizer, so they run concurrently with the rest of the backward pass (dgrad / BatchNorm
+# chain) instead of on its critical path.  In this mode the conv operators return no weight / bias
+# gradient to autograd (which would read or clone the tensors on the main stream while the side
+# stream still writes them); the gradients are attached to ``param.grad`` when the streams are joined
+# at the end of the backward pass, and the parameters' post-accumulate hooks (gradient sync) are
+# fired then.  A parameter used twice in one backward pass (the two discriminator passes of the D
+# update) accumulates in the kernel (second launch: accumulate = 1).
+_async = {"on": False, "stream": None, "pending": {}, "keep": []}
+
+
+def _wgrad_stream():
+    if _async["stream"] is None:
+        _async["stream"] = torch.cuda.Stream()
+    return _async["stream"]
+
+
+def join_wgrad(end_of_backward: bool = True):
+    """Make the current stream wait for the outstanding side-stream weight gradients;
+    ``end_of_backward``: also hand the finished gradients to their parameters."""
+    if _async["stream"] is not None and (_async["keep"] or _async["pending"]):
+        torch.cuda.current_stream().wait_stream(_async["stream"])
+    _async["keep"].clear()
+    if not end_of_backward:
+        return
+    pending, _async["pending"] = _async["pending"], {}
+    for weight, bias, dw, db, want_w, want_b in pending.values():
+        for p, g, want in ((weight, dw, want_w), (bias, db, want_b)):
+            if not want or p is None:
+                continue
+            p.grad = g if p.grad is None else p.grad + g
+            hooks = getattr(p, "_post_accumulate_grad_hooks", None)
+            if hooks:
+                for hook in list(hooks.values()):
+                    hook(p)
+
+
+@contextlib.contextmanager
+def async_weight_grads(on: bool = True):
+    prev, _async["on"] = _async["on"], on
+    try:
+        yield
+    finally:
+        join_wgrad()
+        _async["on"] = prev
+
 
 def begin_step(device=None):
     """Called by the trainer at the start of every step (all ranks): resets per-step numbering and
     re-zeroes the accumulator arena."""
     _colsum_cache.clear()
+    join_wgrad()
     if _peer is not None:
         _peer.reset()
     if device is not None and torch.device(device).type == "cuda":
@@ -329,6 +376,7 @@ class Conv2dFn(torch.autograd.Function):
                 y = torch.empty((d.n, d.oh, d.ow, cout), dtype=torch.bfloat16, device=dev)
             call("sisr_conv_fprop", d, x, wf, bias_used, cfg.act, cfg.leaky_slope, slope, y, None, stats, st)
         ctx.cfg, ctx.d = cfg, d
+        ctx.weight_ref, ctx.bias_ref = weight, bias
         ctx.has_sn = u is not None
         ctx.has_slope = slope is not None
         ctx.skip_params = _skip_param_grads
@@ -377,10 +425,28 @@ class Conv2dFn(torch.autograd.Function):
         if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not ctx.skip_params:
             nbytes = query("sisr_conv_wgrad_fused_workspace_bytes", d)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            dw = torch.empty_like(weight)
-            db = torch.empty(cout, dtype=torch.float32, device=dev)
-            call("sisr_conv_wgrad_fused", d, x, dpre, weight, u, v, sigma if ctx.has_sn else None, dw,
-                 colsum, db, 0, ws, st)
+            sig = sigma if ctx.has_sn else None
+            if _async["on"]:
+                key = weight.data_ptr()
+                prev = _async["pending"].get(key)
+                if prev is None:
+                    dw = torch.empty_like(weight)
+                    db = torch.empty(cout, dtype=torch.float32, device=dev)
+                    _async["pending"][key] = (ctx.weight_ref, ctx.bias_ref, dw, db, ctx.needs_input_grad[1],
+                                              ctx.needs_input_grad[2])
+                else:
+                    dw, db = prev[2], prev[3]
+                side = _wgrad_stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    call("sisr_conv_wgrad_fused", d, x, dpre, weight, u, v, sig, dw, colsum, db,
+                         0 if prev is None else 1, ws, side.cuda_stream)
+                _async["keep"].append((ws, x, dpre, colsum))     # alive until the streams are joined
+                dw = db = None            # delivered to param.grad by join_wgrad()
+            else:
+                dw = torch.empty_like(weight)
+                db = torch.empty(cout, dtype=torch.float32, device=dev)
+                call("sisr_conv_wgrad_fused", d, x, dpre, weight, u, v, sig, dw, colsum, db, 0, ws, st)
             if not ctx.needs_input_grad[1]:
                 dw = None
             if not ctx.needs_input_grad[2]:
@@ -598,6 +664,31 @@ class MSEFn(torch.autograd.Function):
         gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
         call("sisr_mse_bwd", a, b, n, 1.0 / n, gl.contiguous().float().view(1), ga, gb, _stream())
         return ga, gb
+
+
+class LrFromHrFn(torch.autograd.Function):
+    """utils.lr_from_hr: bicubic (align_corners=True) down-sampling + clamp to [-1, 1], NCHW fp32."""
+
+    @staticmethod
+    def forward(ctx, hr, size):
+        _require_cuda(hr, "lr_from_hr")
+        hr = hr.contiguous().float()
+        n, c, h, w = hr.shape
+        oh, ow = int(size[0]), int(size[1])
+        lr = torch.empty((n, c, oh, ow), dtype=torch.float32, device=hr.device)
+        call("sisr_lr_from_hr", hr, lr, n, c, h, w, oh, ow, _stream())
+        ctx.save_for_backward(hr)
+        ctx.size = (oh, ow)
+        return lr
+
+    @staticmethod
+    def backward(ctx, glr):
+        (hr,) = ctx.saved_tensors
+        n, c, h, w = hr.shape
+        oh, ow = ctx.size
+        dhr = torch.empty_like(hr)
+        call("sisr_lr_from_hr_bwd", hr, glr.contiguous().float(), dhr, n, c, h, w, oh, ow, _stream())
+        return dhr, None
 
 
 def bce_loss(p: torch.Tensor, target: float):

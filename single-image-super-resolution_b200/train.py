@@ -36,6 +36,7 @@ class StepConfig:
     dis_list_old_freq: int = 1
     dis_list_old_ratio: float = 0.01
     use_replay: bool = True
+    async_weight_grads: bool = True     # weight-gradient kernels on a side stream (ops.async_weight_grads)
 
 
 class SRGANTrainer:
@@ -88,7 +89,8 @@ class SRGANTrainer:
         curr_fake = fake.detach()
         d_g_z1, d_x, err_d = self.adversarial_loss_d(img_hr, curr_fake, old_fakes)
         err_d = err_d * c.loss_weight_adv_d
-        err_d.backward()
+        with ops.async_weight_grads(c.async_weight_grads):
+            err_d.backward()
         if self.grad_sync is not None:
             self.grad_sync.sync(self.opt_d)
         self.opt_d.step()
@@ -97,7 +99,8 @@ class SRGANTrainer:
         d_g_z2, err_g_adv = self.adversarial_loss_g(fake)
         err_g_adv = err_g_adv * c.loss_weight_adv_g
         err_g_cont = self.content_loss_g(img_hr, fake) * c.loss_weight_cont
-        (err_g_adv + err_g_cont).backward()
+        with ops.async_weight_grads(c.async_weight_grads):
+            (err_g_adv + err_g_cont).backward()
         if self.grad_sync is not None:
             self.grad_sync.sync(self.opt_g)
         self.opt_g.step()

@@ -286,3 +286,28 @@ def test_fused_adam_matches_torch(cuda):
         ref.step(); sched.step(); mine.step()
     for a, b in zip(ref_p, my_p):
         assert rel(b.detach(), a.detach()) < 1e-5
+
+
+def test_lr_from_hr_matches_reference_and_torch(cuda, golden_dir):
+    """utils.lr_from_hr (utils.py:16-31): the reference's own output (golden fixture) and
+    F.interpolate(bicubic, align_corners=True) + clamp on the bench shape; fp32, tolerance 2e-6
+    (the CPU kernel and the CUDA kernel contract their multiply-adds differently)."""
+    import os
+    from sisr_b200 import lr_from_hr
+    g = torch.load(os.path.join(golden_dir, "lr_from_hr.pt"))
+    out = lr_from_hr(g["hr"].cuda(), (4, 4))
+    assert float((out.cpu() - g["lr"]).abs().max()) < 2e-6
+    gen = torch.Generator().manual_seed(77)
+    hr = torch.rand(8, 3, 96, 96, generator=gen) * 2 - 1
+    want = F.interpolate(hr, (24, 24), mode="bicubic", align_corners=True)
+    assert float(want.abs().max()) > 1.0                       # the clamp is exercised
+    got = lr_from_hr(hr.cuda(), (24, 24))
+    assert float((got.cpu() - want.clamp(-1, 1)).abs().max()) < 2e-6
+    # backward (content_loss_on_lr mode): gradient passes where the value was not clamped
+    hr_r = hr.clone().requires_grad_(True)
+    lr_r = F.interpolate(hr_r, (24, 24), mode="bicubic", align_corners=True).clamp(-1, 1)
+    gy = torch.randn(lr_r.shape, generator=gen)
+    lr_r.backward(gy)
+    hr_d = hr.cuda().requires_grad_(True)
+    lr_from_hr(hr_d, (24, 24)).backward(gy.cuda())
+    assert rel(hr_d.grad, hr_r.grad) < 1e-5
