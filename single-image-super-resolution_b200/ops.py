@@ -115,13 +115,39 @@ _arena = _ZeroArena()
 # at the end of the backward pass, and the parameters' post-accumulate hooks (gradient sync) are
 # fired then.  A parameter used twice in one backward pass (the two discriminator passes of the D
 # update) accumulates in the kernel (second launch: accumulate = 1).
-_async = {"on": False, "stream": None, "pending": {}, "keep": []}
+_async = {"on": False, "stream": None, "pending": {}, "keep": [], "uses": {}, "track": False, "ready": []}
+_ASYNC_LAG = 4      # a finished parameter is handed over once this many later launches are queued behind it
 
 
 def _wgrad_stream():
     if _async["stream"] is None:
         _async["stream"] = torch.cuda.Stream()
     return _async["stream"]
+
+
+def _deliver(entry):
+    weight, bias, dw, db, want_w, want_b = entry
+    for p, g, want in ((weight, dw, want_w), (bias, db, want_b)):
+        if not want or p is None:
+            continue
+        p.grad = g if p.grad is None else p.grad + g
+        hooks = getattr(p, "_post_accumulate_grad_hooks", None)
+        if hooks:
+            for hook in list(hooks.values()):
+                hook(p)
+
+
+def _deliver_ready(keep_last: int):
+    """Hand over the parameters whose last launch is at least ``keep_last`` launches old: the main
+    stream waits for the event recorded behind that launch (normally long finished), the gradient
+    lands in ``param.grad`` and the gradient-sync hooks fire while backward is still running."""
+    ready = _async["ready"]
+    while len(ready) > keep_last:
+        key, ev = ready.pop(0)
+        entry = _async["pending"].pop(key, None)
+        if entry is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            _deliver(entry)
 
 
 def join_wgrad(end_of_backward: bool = True):
@@ -132,16 +158,10 @@ def join_wgrad(end_of_backward: bool = True):
     _async["keep"].clear()
     if not end_of_backward:
         return
+    _async["ready"].clear()
     pending, _async["pending"] = _async["pending"], {}
-    for weight, bias, dw, db, want_w, want_b in pending.values():
-        for p, g, want in ((weight, dw, want_w), (bias, db, want_b)):
-            if not want or p is None:
-                continue
-            p.grad = g if p.grad is None else p.grad + g
-            hooks = getattr(p, "_post_accumulate_grad_hooks", None)
-            if hooks:
-                for hook in list(hooks.values()):
-                    hook(p)
+    for entry in pending.values():
+        _deliver(entry)
 
 
 @contextlib.contextmanager
@@ -154,11 +174,13 @@ def async_weight_grads(on: bool = True):
         _async["on"] = prev
 
 
-def begin_step(device=None):
+def begin_step(device=None, track_weight_uses: bool = False):
     """Called by the trainer at the start of every step (all ranks): resets per-step numbering and
     re-zeroes the accumulator arena."""
     _colsum_cache.clear()
     join_wgrad()
+    _async["uses"].clear()
+    _async["track"] = track_weight_uses
     if _peer is not None:
         _peer.reset()
     if device is not None and torch.device(device).type == "cuda":
@@ -377,6 +399,9 @@ class Conv2dFn(torch.autograd.Function):
             call("sisr_conv_fprop", d, x, wf, bias_used, cfg.act, cfg.leaky_slope, slope, y, None, stats, st)
         ctx.cfg, ctx.d = cfg, d
         ctx.weight_ref, ctx.bias_ref = weight, bias
+        if _async["track"] and not _skip_param_grads and (weight.requires_grad or bias.requires_grad):
+            k_ = weight.data_ptr()
+            _async["uses"][k_] = _async["uses"].get(k_, 0) + 1
         ctx.has_sn = u is not None
         ctx.has_slope = slope is not None
         ctx.skip_params = _skip_param_grads
@@ -442,7 +467,15 @@ class Conv2dFn(torch.autograd.Function):
                     call("sisr_conv_wgrad_fused", d, x, dpre, weight, u, v, sig, dw, colsum, db,
                          0 if prev is None else 1, ws, side.cuda_stream)
                 _async["keep"].append((ws, x, dpre, colsum))     # alive until the streams are joined
-                dw = db = None            # delivered to param.grad by join_wgrad()
+                dw = db = None            # delivered to param.grad by _deliver_ready() / join_wgrad()
+                left = _async["uses"].get(key)
+                if left is not None:
+                    _async["uses"][key] = left - 1
+                    if left - 1 == 0:     # every forward use of this parameter has been back-propagated
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        _async["ready"].append((key, ev))
+                        _deliver_ready(_ASYNC_LAG)
             else:
                 dw = torch.empty_like(weight)
                 db = torch.empty(cout, dtype=torch.float32, device=dev)

@@ -29,6 +29,29 @@ class Adam(torch.optim.Optimizer):
             self._dev_state[gi] = st
         return st
 
+    # -- checkpoint interchange with torch.optim.Adam (utils.py:107-112, config.py:296-302) -----------
+    def state_dict(self):
+        """torch.optim.Adam layout: per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` (the step
+        counter lives on the device here; it is copied into every parameter's state on export)."""
+        sd = super().state_dict()
+        for gi, group in enumerate(sd["param_groups"]):
+            st = self._dev_state.get(gi)
+            step = int(st[0].item()) if st is not None else 0
+            for idx in group["params"]:
+                if idx in sd["state"]:
+                    sd["state"][idx]["step"] = torch.tensor(float(step))
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for gi, group in enumerate(self.param_groups):
+            steps = [int(self.state[p]["step"]) for p in group["params"]
+                     if p in self.state and "step" in self.state[p]]
+            dev = next((p.device for p in group["params"] if p.is_cuda), None)
+            if steps and dev is not None:
+                step_t, _ = self._device_scalars(gi, dev)
+                step_t.fill_(max(steps))
+
     @torch.no_grad()
     def step(self, closure=None):
         for gi, group in enumerate(self.param_groups):

@@ -146,7 +146,6 @@ class GradSync:
 
     def _launch(self, plan, b):
         b["ready"] = 0
-        ops.join_wgrad(end_of_backward=False)   # side-stream weight gradients must have landed before packing
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b["params"]]
         torch._foreach_copy_([plan["views"][p] for p in b["params"]], grads)
         if self.world == 1:

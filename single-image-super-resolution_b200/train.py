@@ -82,7 +82,7 @@ class SRGANTrainer:
     def step(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=()):
         """img_hr: (B,3,H,H) fp32 in [-1,1]; img_lr: (B,3,H/s,H/s).  Returns device scalars."""
         c = self.cfg
-        ops.begin_step(img_hr.device)
+        ops.begin_step(img_hr.device, track_weight_uses=c.async_weight_grads)
         fake = self.net_g(img_lr)
 
         self.net_d.zero_grad(set_to_none=True)
@@ -124,6 +124,33 @@ class SRGANTrainer:
                 self.dis_list_old.append(snap)
         self.iteration += 1
         return out
+
+    # -- checkpoint (same dictionary as utils._save, utils.py:107-114) -----------------------------
+    def checkpoint(self, epoch: int = 0) -> dict:
+        return {"epoch": epoch, "net_g": self.net_g.state_dict(), "net_d": self.net_d.state_dict(),
+                "opti_g": self.opt_g.state_dict(), "opti_d": self.opt_d.state_dict(),
+                "dis_list": list(self.dis_list_old)}
+
+    def restore(self, checkpoint: dict) -> int:
+        """Resume as config.py does (config.py:90-92, 296-302, 308-331): non-strict weight loading
+        (``module.`` prefixes of a DataParallel checkpoint are stripped), optimizer state best
+        effort, replay list as saved.  Returns the starting epoch."""
+        def strip(sd):
+            return {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}
+        if "net_g" in checkpoint:
+            self.net_g.load_state_dict(strip(checkpoint["net_g"]), strict=False)
+        if "net_d" in checkpoint:
+            self.net_d.load_state_dict(strip(checkpoint["net_d"]), strict=False)
+        for opt, key in ((self.opt_g, "opti_g"), (self.opt_d, "opti_d")):
+            if key in checkpoint:
+                try:
+                    opt.load_state_dict(checkpoint[key])
+                except Exception as e:  # noqa: BLE001 - mirrors the reference's best-effort load
+                    print("erreur chargement optimizers:", e)
+        dev = next(self.net_g.parameters()).device
+        self.dis_list_old = [t.to(dev) for t in checkpoint.get("dis_list", [])]
+        self._graph = None          # a captured graph holds the old optimizer buffers
+        return int(checkpoint.get("epoch", 0))
 
     # -- CUDA graph of the whole step ----------------------------------------------------------
     def capture(self, img_hr: torch.Tensor, img_lr: torch.Tensor, warmup: int = 2):

@@ -307,3 +307,57 @@ def test_frozen_prefix_trains_only_the_suffix(cuda):
     for k, p in g2.named_parameters():
         changed = bool((p.detach() != before[k]).any())
         assert changed == (not k.startswith("base.")), k
+
+
+def test_checkpoint_resume_and_torch_adam_interchange(cuda):
+    """utils._save dictionary (utils.py:107-114): resume continues exactly where the run stopped, and
+    the optimizer state loads into torch.optim.Adam (and back)."""
+    import sisr_b200 as m
+    seed, shape, feats, strides, mask, lr = 710, (3, 16, 16), [64, 64, 128, 128], [1, 2, 1, 2], 0b00010, 1e-3
+    hrs = [S.synthetic_hr(seed + 10 + i, 4, 16) for i in range(3)]
+    lrs = [O.lr_from_hr(h, (4, 4)) for h in hrs]
+    tr, _ = _build_step(m, seed, shape, feats, strides, mask, lr)
+    for i in range(2):
+        tr.step(hrs[i].cuda(), lrs[i].cuda())
+    ckpt = tr.checkpoint(epoch=7)
+    assert set(ckpt) == {"epoch", "net_g", "net_d", "opti_g", "opti_d", "dis_list"}
+    ckpt = {k: (S.clone_state(v) if k.startswith("net_") else v) for k, v in ckpt.items()}
+    import copy
+    ckpt["opti_g"], ckpt["opti_d"] = copy.deepcopy(ckpt["opti_g"]), copy.deepcopy(ckpt["opti_d"])
+    want = tr.step(hrs[2].cuda(), lrs[2].cuda())
+    tr2, _ = _build_step(m, seed, shape, feats, strides, mask, lr)               # untrained weights
+    ckpt["net_g"] = {"module." + k: v for k, v in ckpt["net_g"].items()}         # saved under DataParallel
+    assert tr2.restore(ckpt) == 7
+    got = tr2.step(hrs[2].cuda(), lrs[2].cuda())
+    for k in ("err_d", "err_g_adv", "err_g_cont"):
+        assert abs(float(got[k]) - float(want[k])) < 5e-3 * abs(float(want[k])), k
+    # optimizer interchange: same keys / shapes as torch.optim.Adam, step counter included
+    params = [torch.nn.Parameter(p.detach().clone()) for p in tr.net_d.parameters()]
+    ref = torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999))
+    ref.load_state_dict(ckpt["opti_d"])
+    st = ref.state[params[0]]
+    assert int(st["step"]) == 2 and st["exp_avg"].shape == params[0].shape
+    tr2.opt_d.load_state_dict(ref.state_dict())
+    assert int(tr2.opt_d._dev_state[0][0].item()) == 2
+
+
+def test_experience_replay_step_vs_oracle(cuda):
+    """train.py:59-71,144-146: replayed old fakes add one discriminator pass each, their BCE terms are
+    SUMMED into the D loss; the replay list lives on the GPU in bf16."""
+    import sisr_b200 as m
+    seed, shape, feats, strides, mask, lr = 720, (3, 16, 16), [64, 64, 128, 128], [1, 2, 1, 2], 0b00010, 1e-3
+    tr, (g_st, d_st, v_st) = _build_step(m, seed, shape, feats, strides, mask, lr)
+    hr = S.synthetic_hr(seed + 10, 4, 16)
+    lr_img = O.lr_from_hr(hr, (4, 4))
+    old = [(S.synthetic_hr(seed + 20 + i, 4, 16) * 0.5).to(torch.bfloat16).float() for i in range(2)]
+    out = tr.step(hr.cuda(), lr_img.cuda(), [o.cuda() for o in old])
+    ref = O.train_step(g_st, d_st, v_st, hr, lr_img, d_strides=strides, vgg_mask=mask,
+                       opt_g=O.AdamState(O.trainable_names(g_st), lr),
+                       opt_d=O.AdamState(O.trainable_names(d_st), lr), old_fakes=old)
+    for k in ("err_d", "err_g_adv", "err_g_cont"):
+        assert abs(float(out[k]) - ref[k]) < 3e-2 * abs(ref[k]), (k, float(out[k]), ref[k])
+    assert abs(float(out["d_g_z1"]) - ref["d_g_z1"]) < 3e-2 * abs(ref["d_g_z1"])      # sum over 3 fake batches
+    # bookkeeping of train_iteration: the list grows by one bf16 GPU tensor per step
+    tr.cfg.use_replay = True
+    tr.train_iteration(hr.cuda(), lr_img.cuda())
+    assert len(tr.dis_list_old) == 1 and tr.dis_list_old[0].dtype == torch.bfloat16 and tr.dis_list_old[0].is_cuda
