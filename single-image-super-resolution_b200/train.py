@@ -37,6 +37,7 @@ class StepConfig:
     dis_list_old_ratio: float = 0.01
     use_replay: bool = True
     async_weight_grads: bool = True     # weight-gradient kernels on a side stream (ops.async_weight_grads)
+    overlap_real_features: bool = True  # MaskedVGG(real) on a side stream, concurrent with G and the D update
 
 
 class SRGANTrainer:
@@ -53,6 +54,7 @@ class SRGANTrainer:
         self.grad_sync = grad_sync      # parallel.GradSync or None
         self._graph = None
         self._static = None
+        self._side = None
 
     # -- losses (train.py:128-186) -----------------------------------------------------------
     def adversarial_loss_d(self, real, curr_fake, old_fakes):
@@ -73,16 +75,29 @@ class SRGANTrainer:
         err, d_g_z2 = ops.bce_loss(out, self.cfg.real_label)
         return d_g_z2, err
 
-    def content_loss_g(self, real, fake):
-        a = self.extractor(real)
+    def content_loss_g(self, real, fake, feat_real=None):
+        a = self.extractor(real) if feat_real is None else feat_real
         b = self.extractor(fake)
         return ops.mse_loss(a, b)
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
 
     # -- one iteration -----------------------------------------------------------------------
     def step(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=()):
         """img_hr: (B,3,H,H) fp32 in [-1,1]; img_lr: (B,3,H/s,H/s).  Returns device scalars."""
         c = self.cfg
         ops.begin_step(img_hr.device, track_weight_uses=c.async_weight_grads)
+        # the content-loss features of the REAL batch depend on nothing else in the step: they run on a
+        # side stream, filling the SMs that the small generator / discriminator kernels leave idle
+        feat_real = side = None
+        if c.overlap_real_features and img_hr.is_cuda:
+            side = self._side_stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                feat_real = self.extractor(img_hr)
         fake = self.net_g(img_lr)
 
         self.net_d.zero_grad(set_to_none=True)
@@ -98,7 +113,9 @@ class SRGANTrainer:
         self.net_g.zero_grad(set_to_none=True)
         d_g_z2, err_g_adv = self.adversarial_loss_g(fake)
         err_g_adv = err_g_adv * c.loss_weight_adv_g
-        err_g_cont = self.content_loss_g(img_hr, fake) * c.loss_weight_cont
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        err_g_cont = self.content_loss_g(img_hr, fake, feat_real) * c.loss_weight_cont
         with ops.async_weight_grads(c.async_weight_grads):
             (err_g_adv + err_g_cont).backward()
         if self.grad_sync is not None:
