@@ -199,7 +199,7 @@ def time_conv_kernel(dev, n, h, cin, cout, with_stats):
 
 
 def time_dominant_kernel(dev, batch):
-    """igemm_t_kernel (17.7 % of the step, profiles/r1_step_launches_b64_t33.csv) on its most frequent
+    """igemm_t_kernel (18.6 % of the step's kernel time, profiles/r1_step_launches_b64_final.csv) on its most frequent
     shape: the generator trunk conv 64->64 @24x24 with fused BN statistics (33 of its 93 launches)."""
     return time_conv_kernel(dev, batch, 24, 64, 64, True)
 
@@ -367,8 +367,8 @@ def run_ours(args):
                      "traffic": 4831488,
                      "kernel": "igemm_t_kernel: " + dom["kernel"], "ms_per_launch": dom["ms"],
                      "peak_source": peaks["source"] + " (burst: kernel timed alone)",
-                     "share_of_step": "igemm_t_kernel = 17.7 % of the step's kernel time "
-                                      "(profiles/r1_step_launches_b64_t33.csv)",
+                     "share_of_step": "igemm_t_kernel = 18.6 % of the step's kernel time "
+                                      "(profiles/r1_step_launches_b64_final.csv)",
                      "timing": "12 back-to-back launches per CUDA graph over 3 rotating buffer sets (tensors "
                                "L2-resident as in the step), CUDA events on the replaying stream"},
         "roofline_other": [{"kernel": o["kernel"], "achieved": o["tflops"], "unit": "TFLOP/s",
