@@ -113,6 +113,14 @@ int sisr_conv_fprop(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
  * fprop wrote it (pixel-shuffled when ps_r = 2). */
 int sisr_conv_dgrad(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf16* w_fprop,
                     const sisr_bf16* w_dgrad, sisr_bf16* dx, void* stream);
+/* dgrad with the activation backward of the conv's INPUT tensor fused into the store:
+ * dx = conv_transpose(dy) * (x > 0 ? 1 : mask_slope), mask = x (the input of this conv, which is the
+ * ReLU-family output of the previous layer; vgg19.features ReLU, model_content_extractor.py:43).
+ * Only where sisr_conv_dgrad_fuses_mask(d) = 1 (tensor-core path). */
+int sisr_conv_dgrad_fuses_mask(const sisr_conv_desc* d);
+int sisr_conv_dgrad_masked(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf16* w_fprop,
+                           const sisr_bf16* w_dgrad, sisr_bf16* dx, const sisr_bf16* mask, float mask_slope,
+                           void* stream);
 /* g_prepared: fp32 [cout',k,k,cin] (overwritten); dbias_perm: fp32 [cout'] nullable.
  * workspace: sisr_conv_wgrad_workspace_bytes(d) bytes (split-K partials), may be NULL if that is 0. */
 size_t sisr_conv_wgrad_workspace_bytes(const sisr_conv_desc* d);

@@ -182,12 +182,16 @@ int sisr_conv_fprop(const sisr_conv_desc* d, const sisr_bf16* x, const sisr_bf16
   return 0;
 }
 
-int sisr_conv_dgrad(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf16* w_fprop,
-                    const sisr_bf16* w_dgrad, sisr_bf16* dx, void* s) {
+static int conv_dgrad_impl(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf16* w_fprop,
+                           const sisr_bf16* w_dgrad, sisr_bf16* dx, const sisr_bf16* mask, float mask_slope,
+                           void* s) {
   if (!desc_ok(d)) return fail(1, "conv_dgrad: inconsistent descriptor");
   const bool even = (d->h % 2 == 0) && (d->w % 2 == 0);
+  if (mask && !(tc_shape(d) && w_dgrad && (d->stride == 1 || even) && d->ps_r < 2))
+    return fail(1, "conv_dgrad_masked: only on the tensor-core path (see sisr_conv_dgrad_fuses_mask)");
   if (tc_shape(d) && w_dgrad && (d->stride == 1 || even)) {
     IgemmProblem p{};
+    p.mask = B(mask); p.mask_slope = mask_slope;
     p.w = B(w_dgrad); p.Cout = d->cin; p.Ktot = 9 * d->cout;
     p.out = B(dx); p.OH = d->h; p.OW = d->w; p.ldc = d->cin; p.ps_c = 0;
     p.bias = nullptr; p.act = ACT_NONE; p.stats = nullptr;
@@ -267,6 +271,20 @@ int sisr_conv_dgrad(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf1
     }
   }
   return wrap(conv_dgrad_simt(simt_of(d), B(dy), B(w_fprop), B(dx), S(s)), "conv_dgrad_simt");
+}
+int sisr_conv_dgrad(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf16* w_fprop,
+                    const sisr_bf16* w_dgrad, sisr_bf16* dx, void* s) {
+  return conv_dgrad_impl(d, dy, w_fprop, w_dgrad, dx, nullptr, 0.f, s);
+}
+int sisr_conv_dgrad_fuses_mask(const sisr_conv_desc* d) {
+  const bool even = d && (d->h % 2 == 0) && (d->w % 2 == 0);
+  return desc_ok(d) && tc_shape(d) && (d->stride == 1 || even) && d->ps_r < 2 ? 1 : 0;
+}
+int sisr_conv_dgrad_masked(const sisr_conv_desc* d, const sisr_bf16* dy, const sisr_bf16* w_fprop,
+                           const sisr_bf16* w_dgrad, sisr_bf16* dx, const sisr_bf16* mask, float mask_slope,
+                           void* s) {
+  if (!mask) return fail(1, "conv_dgrad_masked: null mask");
+  return conv_dgrad_impl(d, dy, w_fprop, w_dgrad, dx, mask, mask_slope, s);
 }
 
 size_t sisr_conv_wgrad_workspace_bytes(const sisr_conv_desc* d) {

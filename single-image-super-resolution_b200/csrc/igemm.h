@@ -47,6 +47,8 @@ struct IgemmProblem {
   int act;                 // Act
   float slope;             // ACT_LEAKY
   const float* slope_ptr;  // ACT_PRELU (single learnable slope)
+  const __nv_bfloat16* mask;  // nullable, indexed like `out`: out = (mask > 0) ? value : value * mask_slope
+  float mask_slope;           // (ReLU backward of the tensor this dgrad feeds, fused into the store)
   float* stats;            // [stats_rows][2*Cout]: row r = {sum, sum of squares} of the stored bf16 values
                            // over the tiles of CTA r (rows >= grid are zeroed), or nullptr
   int stats_rows;          // >= igemm_max_ctas()

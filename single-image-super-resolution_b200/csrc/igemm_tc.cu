@@ -47,6 +47,8 @@ struct EpiParams {
   const float* slope_ptr;
   float* stats;
   int stats_rows;
+  const __nv_bfloat16* mask;
+  float mask_slope;
 };
 
 struct KParams {
@@ -134,11 +136,26 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t tmem_
       oy = gh * e.osy + e.opy;
       ox = gw * e.osx + e.opx;
     }
+    const size_t off = (static_cast<size_t>(n_img * e.OH + oy) * e.OW + ox) * e.ldc + ch;
+    if (e.mask && valid) {   // fused activation backward of the tensor this gradient belongs to
+      const uint4* m4 = reinterpret_cast<const uint4*>(e.mask + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 mq = __ldg(m4 + q);
+        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mq);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 mf = __bfloat1622float2(mh[j]);
+          if (!(mf.x > 0.f)) v[q * 8 + 2 * j] *= e.mask_slope;
+          if (!(mf.y > 0.f)) v[q * 8 + 2 * j + 1] *= e.mask_slope;
+        }
+      }
+    }
     uint32_t packed[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
     if (valid) {
-      __nv_bfloat16* dst = e.out + (static_cast<size_t>(n_img * e.OH + oy) * e.OW + ox) * e.ldc + ch;
+      __nv_bfloat16* dst = e.out + off;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -507,7 +524,20 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
                 const int gw = rem - gh * p.GW;
                 opix = static_cast<size_t>(n_img * e.OH + gh * e.osy + e.opy) * e.OW + gw * e.osx + e.opx;
               }
-              const uint4 val = *reinterpret_cast<const uint4*>(stage + row * row_words + seg * 4);
+              uint4 val = *reinterpret_cast<const uint4*>(stage + row * row_words + seg * 4);
+              if (e.mask) {
+                const uint4 mq = __ldg(reinterpret_cast<const uint4*>(e.mask + opix * e.ldc + seg * 8));
+                const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mq);
+                __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 mf = __bfloat1622float2(mh[j]);
+                  float2 vf = __bfloat1622float2(vh[j]);
+                  if (!(mf.x > 0.f)) vf.x *= e.mask_slope;
+                  if (!(mf.y > 0.f)) vf.y *= e.mask_slope;
+                  vh[j] = __floats2bfloat162_rn(vf.x, vf.y);
+                }
+              }
               *reinterpret_cast<uint4*>(e.out + opix * e.ldc + seg * 8) = val;
             }
           }
@@ -836,6 +866,7 @@ void fill_epi(EpiParams& e, const IgemmProblem& p) {
   e.ps_c = p.ps_c;
   e.bias = p.bias; e.act = p.act; e.slope = p.slope; e.slope_ptr = p.slope_ptr;
   e.stats = p.stats; e.stats_rows = p.stats_rows;
+  e.mask = p.mask; e.mask_slope = p.mask_slope;
 }
 
 }  // namespace
@@ -852,8 +883,9 @@ bool igemm_supported(const IgemmProblem& p) {
   if (p.ldc % 8) return false;
   if (p.ps_c > 0 && (p.ps_c % 32)) return false;
   if ((reinterpret_cast<uintptr_t>(p.x) & 15) || (reinterpret_cast<uintptr_t>(p.w) & 15) ||
-      (reinterpret_cast<uintptr_t>(p.out) & 15))
+      (reinterpret_cast<uintptr_t>(p.out) & 15) || (reinterpret_cast<uintptr_t>(p.mask) & 15))
     return false;
+  if (p.mask && p.ps_c > 0) return false;
   return true;
 }
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -26,6 +27,14 @@ _skip_param_grads = False
 # {data_ptr of a gradient tensor: (that tensor, its per-channel column sums)}: lets the kernel that
 # writes a conv's output gradient also deliver the conv's bias gradient (cleared every step)
 _colsum_cache = {}
+# ReLU backward fused into the NEXT layer's dgrad (frozen VGG stack): a conv whose output went through
+# a fused ReLU and that needs no parameter gradient registers its output here; the conv that consumes
+# exactly that tensor masks its input gradient with it (sisr_conv_dgrad_masked) and lists the result
+# in _premasked, so that the producer skips its own activation-backward pass.  ReLU only: the mask is
+# idempotent, so a gradient that reaches the producer through a second path is still handled right.
+_relu_outputs = {}
+_premasked = {}
+_NO_MASK_FUSION = bool(os.environ.get("SISR_DIAG_NO_MASK_FUSION"))     # A-B timing
 
 
 @contextlib.contextmanager
@@ -178,6 +187,8 @@ def begin_step(device=None, track_weight_uses: bool = False):
     """Called by the trainer at the start of every step (all ranks): resets per-step numbering and
     re-zeroes the accumulator arena."""
     _colsum_cache.clear()
+    _relu_outputs.clear()
+    _premasked.clear()
     join_wgrad()
     _async["uses"].clear()
     _async["track"] = track_weight_uses
@@ -399,6 +410,15 @@ class Conv2dFn(torch.autograd.Function):
             call("sisr_conv_fprop", d, x, wf, bias_used, cfg.act, cfg.leaky_slope, slope, y, None, stats, st)
         ctx.cfg, ctx.d = cfg, d
         ctx.weight_ref, ctx.bias_ref = weight, bias
+        src = _relu_outputs.get(x.data_ptr())
+        ctx.input_is_relu = bool(src is not None and src.shape == x.shape and need_dx and not cfg.out_nchw_f32
+                                 and not _NO_MASK_FUSION
+                                 and query("sisr_conv_dgrad_fuses_mask", d))
+        if (cfg.act == ACT_RELU and need_dx and not cfg.out_nchw_f32 and cfg.ps_r != 2 and
+                (_skip_param_grads or not (weight.requires_grad or bias.requires_grad))):
+            if len(_relu_outputs) > 256:      # callers that never reach begin_step()
+                _relu_outputs.clear()
+            _relu_outputs[y.data_ptr()] = y
         if _async["track"] and not _skip_param_grads and (weight.requires_grad or bias.requires_grad):
             k_ = weight.data_ptr()
             _async["uses"][k_] = _async["uses"].get(k_, 0) + 1
@@ -426,6 +446,8 @@ class Conv2dFn(torch.autograd.Function):
                 call("sisr_tanh_bwd_nchw_to_nhwc", gy.float(), y, dpre, d.n, cout, d.oh, d.ow, st)
             else:
                 call("sisr_nchw_f32_to_nhwc_bf16", gy.float(), dpre, d.n, cout, d.oh, d.ow, st)
+        elif cfg.act == ACT_RELU and _premasked.pop(gy.data_ptr(), None) is not None:
+            dpre = gy                      # the consumer's dgrad already applied this layer's ReLU mask
         elif cfg.act != ACT_NONE:
             dpre = torch.empty_like(gy)
             want_ds = cfg.act == ACT_PRELU and ctx.needs_input_grad[5] and not ctx.skip_params
@@ -445,7 +467,11 @@ class Conv2dFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            call("sisr_conv_dgrad", d, dpre, wf, wd, dx, st)
+            if ctx.input_is_relu:
+                call("sisr_conv_dgrad_masked", d, dpre, wf, wd, dx, x, 0.0, st)
+                _premasked[dx.data_ptr()] = dx
+            else:
+                call("sisr_conv_dgrad", d, dpre, wf, wd, dx, st)
         dw = db = None
         if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not ctx.skip_params:
             nbytes = query("sisr_conv_wgrad_fused_workspace_bytes", d)
