@@ -56,6 +56,38 @@ constexpr int kThreads = 256;
 constexpr int kTileQ = 128;    // pixels per tile (thin-in, wgrad)
 constexpr int kLdC = 72;       // bf16 row stride of a staged [pixels][64 channels] tile (144 B)
 
+// Stage the pixels [w0, w0 + count) (flattened N*H*W order, 3 bf16 each, contiguous in memory) of a
+// 3-channel tensor into shared memory with 16-byte loads; pixels outside [0, npix) are left unset
+// (the im2col below only reads pixels of valid taps).  Returns nothing; win[(q - w0) * 3 + c].
+__device__ __forceinline__ void stage_window3(const __nv_bfloat16* __restrict__ src, long long npix,
+                                              long long w0, int count, __nv_bfloat16* win) {
+  // byte range of the window, widened to 16-byte boundaries of the global buffer
+  const long long lo = (w0 < 0 ? 0 : w0) * 6;
+  long long hi = (w0 + count) * 6;
+  if (hi > npix * 6) hi = npix * 6;
+  if (hi <= lo) return;
+  const uintptr_t gbase = reinterpret_cast<uintptr_t>(src);
+  const long long a0 = static_cast<long long>(((gbase + lo) & ~static_cast<uintptr_t>(15)) - gbase);
+  // destination byte offset of global byte a0 inside `win` is (a0 - w0*6); may be negative by < 16:
+  // the window buffer has 16 bytes of slack in front (see callers)
+  const long long tot = static_cast<long long>(npix) * 6;
+  for (long long a = a0 + threadIdx.x * 16LL; a < hi; a += blockDim.x * 16LL) {
+    const char* g = reinterpret_cast<const char*>(src) + a;
+    char* d = reinterpret_cast<char*>(win) + (a - w0 * 6);
+    if (a >= 0 && a + 16 <= tot) {
+      const uint4 v = *reinterpret_cast<const uint4*>(g);
+      // shared destination is only 2-byte aligned in general: store as 8 halves
+      const unsigned short* h = reinterpret_cast<const unsigned short*>(&v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) reinterpret_cast<unsigned short*>(d)[i] = h[i];
+    } else {
+      for (int i = 0; i < 16 && a + i < tot; i += 2)
+        if (a + i >= 0)
+          *reinterpret_cast<unsigned short*>(d + i) = *reinterpret_cast<const unsigned short*>(g + i);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ thin-in: 3 -> 64, k x k
 // GEMM per 128-pixel tile: Y[128, 64] = Xim[128, KP] * W[64, KP]^T, KP = k*k*3 zero-padded.
 // w: [CW][k*k][3] bf16; flip: the tap at position t uses w[.][k*k-1-t][.] (transposed conv).
@@ -69,6 +101,7 @@ thin_in_mma_kernel(ThinConv c, const __nv_bfloat16* __restrict__ x, const __nv_b
   __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [64][LDK]
   __nv_bfloat16* Xs = Ws + 64 * LDK;                                // [128][LDK]
   __nv_bfloat16* Cs = Xs + kTileQ * LDK;                            // [128][kLdC]
+  __nv_bfloat16* Win = Cs + kTileQ * kLdC + 8;                      // input window (+16 B slack in front)
   const int T = c.k * c.k, KT = T * 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cwb = blockIdx.y * 64;
@@ -86,21 +119,24 @@ thin_in_mma_kernel(ThinConv c, const __nv_bfloat16* __restrict__ x, const __nv_b
     }
     Ws[i] = v;
   }
-  {  // im2col of the tile: two threads per pixel, alternating taps
+  const int reach = c.pad * (c.W + 1);                 // farthest tap in flattened pixels
+  const long long win0 = q0 - reach;
+  stage_window3(x, npix, win0, kTileQ + 2 * reach, Win);
+  __syncthreads();
+  {  // im2col of the tile from the staged window: two threads per pixel, alternating taps
     const int ql = tid >> 1, half = tid & 1;
     const long long q = q0 + ql;
     const bool valid = q < npix;
     const long long qq = valid ? q : 0;
     const int ow = static_cast<int>(qq % c.W);
     const int oh = static_cast<int>((qq / c.W) % c.H);
-    const __nv_bfloat16* xim = x + (qq - (static_cast<long long>(oh) * c.W + ow)) * 3;
     __nv_bfloat16* row = Xs + ql * LDK;
     for (int tap = half; tap < T; tap += 2) {
       const int kh = tap / c.k, kw = tap - kh * c.k;
       const int ih = oh - c.pad + kh, iw = ow - c.pad + kw;
       __nv_bfloat16 v0 = zero, v1 = zero, v2 = zero;
       if (valid && ih >= 0 && ih < c.H && iw >= 0 && iw < c.W) {
-        const __nv_bfloat16* p = xim + (static_cast<size_t>(ih) * c.W + iw) * 3;
+        const __nv_bfloat16* p = Win + (ql + reach + (kh - c.pad) * c.W + (kw - c.pad)) * 3;
         v0 = p[0]; v1 = p[1]; v2 = p[2];
       }
       row[tap * 3] = v0; row[tap * 3 + 1] = v1; row[tap * 3 + 2] = v2;
@@ -416,6 +452,8 @@ int set_smem(K kernel, int bytes, int* configured) {
 }
 
 constexpr int kSmemLimit = 220 * 1024;
+// staged input window of thin_in / thin_wgrad: 128 pixels + the reach of the farthest tap on both sides
+int thin_window_bytes(const ThinConv& c) { return (kTileQ + 2 * c.pad * (c.W + 1)) * 6 + 48; }
 
 int thin_out_rows(const ThinConv& c) {
   for (int r = 4; r >= 1; r >>= 1) {
@@ -429,7 +467,10 @@ int thin_out_rows(const ThinConv& c) {
 
 const char* thin_last_error() { return g_err; }
 
-bool thin_in_supported(const ThinConv& c) { return c.CS == 3 && c.CW % 64 == 0 && (c.k == 3 || c.k == 9); }
+bool thin_in_supported(const ThinConv& c) {
+  return c.CS == 3 && c.CW % 64 == 0 && (c.k == 3 || c.k == 9) &&
+         ((64 + kTileQ) * ((c.k == 3 ? 32 : 256) + 8) + kTileQ * kLdC) * 2 + thin_window_bytes(c) <= kSmemLimit;
+}
 bool thin_out_supported(const ThinConv& c) {
   return c.CS == 3 && c.CW == 64 && c.k == 3 &&
          (8 * (9 * 64 + 8) + 3 * (c.W + 2) * kLdC) * 2 <= kSmemLimit;
@@ -443,11 +484,13 @@ int thin_in_conv(const ThinConv& c, const __nv_bfloat16* x, const __nv_bfloat16*
   dim3 grid(static_cast<unsigned>((npix + kTileQ - 1) / kTileQ), c.CW / 64);
   if (c.k == 3) {
     constexpr int KP = 32;
-    const int smem = ((64 + kTileQ) * (KP + 8) + kTileQ * kLdC) * 2;
+    const int smem = ((64 + kTileQ) * (KP + 8) + kTileQ * kLdC) * 2 + thin_window_bytes(c);
+    static int configured = 0;
+    if (int rc = set_smem(thin_in_mma_kernel<KP>, smem, &configured)) return rc;
     thin_in_mma_kernel<KP><<<grid, kThreads, smem, s>>>(c, x, w, bias, act, slope, slope_ptr, flip, y);
   } else {
     constexpr int KP = 256;
-    const int smem = ((64 + kTileQ) * (KP + 8) + kTileQ * kLdC) * 2;
+    const int smem = ((64 + kTileQ) * (KP + 8) + kTileQ * kLdC) * 2 + thin_window_bytes(c);
     static int configured = 0;
     if (int rc = set_smem(thin_in_mma_kernel<KP>, smem, &configured)) return rc;
     thin_in_mma_kernel<KP><<<grid, kThreads, smem, s>>>(c, x, w, bias, act, slope, slope_ptr, flip, y);
