@@ -361,3 +361,45 @@ def test_experience_replay_step_vs_oracle(cuda):
     tr.cfg.use_replay = True
     tr.train_iteration(hr.cuda(), lr_img.cuda())
     assert len(tr.dis_list_old) == 1 and tr.dis_list_old[0].dtype == torch.bfloat16 and tr.dis_list_old[0].is_cuda
+
+
+def test_progressive_x8_step_at_256_vs_oracle(cuda):
+    """BASELINE.json configs[4]: x8 = GeneratorSuffix(GeneratorSuffix(Generator)) on 256x256 HR patches
+    (LR 32x32), D at (3,256,256) (fc_in = 131 072), MaskedVGG54 - one full step at batch 2 against the
+    CPU oracle; also configs[3]: the trunk frozen (freeze_prefix/upscale/end) in a second trainer."""
+    import sisr_b200 as m
+    seed, shape, feats, strides, mask, lr = 730, (3, 256, 256), [64, 64, 128, 128, 256, 256, 512, 512], \
+        [1, 2, 1, 2, 1, 2, 1, 2], 0b10000, 1e-4
+    g_st = S.generator_state(seed, n_blocks=2, n_suffix=2)
+    d_st = S.discriminator_state(seed + 1, shape, feats, strides)
+    v_st = S.vgg_state(seed + 2, mask)
+    net_g = m.GeneratorSuffix(m.GeneratorSuffix(m.Generator(2, 64, 256, [2], use_sn=True)))
+    net_d = m.Discriminator(shape, feats, strides)
+    assert net_d.fc_in == 131072
+    ext = m.MaskedVGG(mask)
+    torch.nn.Module.load_state_dict(net_g, S.clone_state(g_st), strict=True)
+    torch.nn.Module.load_state_dict(net_d, S.clone_state(d_st), strict=True)
+    torch.nn.Module.load_state_dict(ext, S.clone_state(v_st), strict=True)
+    tr = m.SRGANTrainer(net_g.cuda(), net_d.cuda(), ext.cuda(), m.StepConfig(lr=lr, use_replay=False))
+    hr = S.synthetic_hr(seed + 5, 2, 256)
+    lr_img = O.lr_from_hr(hr, (32, 32))
+    out = tr.step(hr.cuda(), lr_img.cuda())
+    assert out["fake"].shape == (2, 3, 256, 256)
+    ref = O.train_step(g_st, d_st, v_st, hr, lr_img, d_strides=strides, vgg_mask=mask,
+                       opt_g=O.AdamState(O.trainable_names(g_st), lr),
+                       opt_d=O.AdamState(O.trainable_names(d_st), lr))
+    assert O.psnr(out["fake"].float().cpu(), ref["fake"]) >= 50.0
+    for k in ("err_d", "err_g_adv", "err_g_cont"):
+        assert abs(float(out[k]) - ref[k]) < 2e-2 * abs(ref[k]), (k, float(out[k]), ref[k])
+    # configs[3]: x2 weights wrapped and frozen - only the new suffix stage trains
+    g1 = m.Generator(2, 64, 256, [2], use_sn=True)
+    g2 = m.GeneratorSuffix(g1, freeze_prefix=True, freeze_upscale=True, freeze_end=True).cuda()
+    trainable = [k for k, p in g2.named_parameters() if p.requires_grad]
+    assert sorted(trainable) == ["upscale.0.bias", "upscale.0.weight_orig", "upscale.2.weight"]
+    d2 = m.Discriminator((3, 32, 32), [64, 64], [1, 2]).cuda()
+    tr2 = m.SRGANTrainer(g2, d2, m.MaskedVGG(0b00010).cuda(), m.StepConfig(lr=1e-3, use_replay=False))
+    before = {k: p.detach().clone() for k, p in g2.named_parameters()}
+    hr2 = S.synthetic_hr(seed + 6, 4, 32)
+    tr2.step(hr2.cuda(), O.lr_from_hr(hr2, (8, 8)).cuda())
+    for k, p in g2.named_parameters():
+        assert bool((p.detach() != before[k]).any()) == (not k.startswith("base.")), k
