@@ -198,10 +198,75 @@ def time_conv_kernel(dev, n, h, cin, cout, with_stats):
             "flops": flops, "ms": us * 1e-3, "tflops": flops / (us * 1e-6) / 1e12}
 
 
+def time_conv_dgrad(dev, n, h, cin, cout, stride=1, ps=0):
+    """Data-gradient launch of a conv layer through the C ABI (same graph timing)."""
+    import torch
+    from sisr_b200 import _lib
+    oh = (h + 2 - 3) // stride + 1
+    d = _lib.ConvDesc(n, h, h, cin, oh, oh, cout, 3, stride, 1, ps)
+    sets = []
+    for _ in range(3):
+        wf = (torch.randn(cout, 3, 3, cin, device=dev) * 0.02).to(torch.bfloat16)
+        wd = (torch.randn(cin, 3, 3, cout, device=dev) * 0.02).to(torch.bfloat16)
+        shp = (n, oh * 2, oh * 2, cout // 4) if ps == 2 else (n, oh, oh, cout)
+        dy = torch.randn(*shp, device=dev).to(torch.bfloat16)
+        dx = torch.empty(n, h, h, cin, device=dev, dtype=torch.bfloat16)
+        sets.append((wf, wd, dy, dx))
+
+    def launch(i, st):
+        wf, wd, dy, dx = sets[i % 3]
+        _lib.call("sisr_conv_dgrad", d, dy, wf, wd, dx, st)
+    us = _graph_time_us(launch)
+    flops = 2.0 * n * oh * oh * cout * 9 * cin
+    return {"kernel": "dgrad of conv3x3 %d->%d s%d @%dx%d" % (cin, cout, stride, h, h), "flops": flops,
+            "ms": us * 1e-3, "tflops": flops / (us * 1e-6) / 1e12}
+
+
 def time_dominant_kernel(dev, batch):
-    """igemm_t_kernel (18.6 % of the step's kernel time, profiles/r1_step_launches_b64_final.csv) on its most frequent
-    shape: the generator trunk conv 64->64 @24x24 with fused BN statistics (33 of its 93 launches)."""
-    return time_conv_kernel(dev, batch, 24, 64, 64, True)
+    """igemm_t_kernel (18.6 % of the step's kernel time, profiles/r1_step_launches_b64_final.csv) over
+    ALL of its 93 launches per step: every distinct (shape, direction) it serves is timed and weighted by
+    its launch count; achieved = sum of algorithmic FLOPs / sum of launch durations."""
+    import torch
+    from sisr_b200 import _lib
+
+    def fwd(h, cin, cout, stats, stride=1):
+        sets = []
+        oh = (h + 2 - 3) // stride + 1
+        d = _lib.ConvDesc(batch, h, h, cin, oh, oh, cout, 3, stride, 1, 0)
+        for _ in range(3):
+            x = torch.randn(batch, h, h, cin, device=dev).to(torch.bfloat16)
+            wt = (torch.randn(cout, 3, 3, cin, device=dev) * 0.02).to(torch.bfloat16)
+            y = torch.empty(batch, oh, oh, cout, device=dev, dtype=torch.bfloat16)
+            st_ = torch.empty(_lib.query("sisr_stats_rows"), 2 * cout, device=dev) if stats else None
+            sets.append((x, wt, y, st_))
+        bias = torch.zeros(cout, device=dev)
+
+        def launch(i, st):
+            x, wt, y, st_ = sets[i % 3]
+            _lib.call("sisr_conv_fprop", d, x, wt, bias, 0, 0.0, None, y, None, st_, st)
+        us = _graph_time_us(launch)
+        flops = 2.0 * batch * oh * oh * cout * 9 * cin
+        return {"kernel": "conv3x3 %d->%d s%d @%dx%d%s" % (cin, cout, stride, h, h, " +BN stats" if stats else ""),
+                "flops": flops, "ms": us * 1e-3, "tflops": flops / (us * 1e-6) / 1e12}
+
+    parts = [  # (launches per step, measurement)
+        (33, fwd(24, 64, 64, True)), (33, time_conv_dgrad(dev, batch, 24, 64, 64)),
+        (2, fwd(96, 64, 64, False)), (1, time_conv_dgrad(dev, batch, 96, 64, 64)),
+        (2, fwd(48, 64, 128, False)), (1, time_conv_dgrad(dev, batch, 48, 64, 128)),
+        (2, fwd(48, 128, 128, False)), (1, time_conv_dgrad(dev, batch, 48, 128, 128)),
+        (1, time_conv_dgrad(dev, batch, 24, 128, 256)),
+        (3, fwd(48, 64, 128, True)), (3, time_conv_dgrad(dev, batch, 48, 64, 128)),
+        (3, time_conv_dgrad(dev, batch, 24, 128, 256)),
+        (3, fwd(96, 64, 64, True, 2)), (3, fwd(48, 128, 128, True, 2)),
+        (2, time_conv_dgrad(dev, batch, 48, 64, 256, 1, 2)),
+    ]
+    flops = sum(c * m["flops"] for c, m in parts)
+    ms = sum(c * m["ms"] for c, m in parts)
+    launches = sum(c for c, _ in parts)
+    return {"kernel": "all %d launches per step (15 shape/direction classes, launch-count weighted)" % launches,
+            "flops": flops / launches, "ms": ms / launches, "tflops": flops / (ms * 1e-3) / 1e12,
+            "classes": [{"launches": c, "kernel": m["kernel"], "us": m["ms"] * 1e3, "tflops": m["tflops"]}
+                        for c, m in parts]}
 
 
 def time_hbm_kernels(dev, batch):
@@ -362,10 +427,12 @@ def run_ours(args):
         "gpu_launches": (launches_per_step or 0) * args.steps,
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_burst"],
                      "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["bf16_burst"],
-                     # dram__bytes_read + write of one launch, ncu --set full (profiles/r1_ncu_trunk_conv.txt):
-                     # 4.83 MB read (the input activation, cold), 0 written back (the output stays in L2)
+                     # dram__bytes_read + write of one launch of the most frequent class (trunk conv), ncu
+                     # --set full (profiles/r1_ncu_trunk_conv.txt): 4.83 MB read (the input activation,
+                     # cold), 0 written back (the output stays in L2)
                      "traffic": 4831488,
                      "kernel": "igemm_t_kernel: " + dom["kernel"], "ms_per_launch": dom["ms"],
+                     "flops_per_launch": dom["flops"], "classes": dom["classes"],
                      "peak_source": peaks["source"] + " (burst: kernel timed alone)",
                      "share_of_step": "igemm_t_kernel = 18.6 % of the step's kernel time "
                                       "(profiles/r1_step_launches_b64_final.csv)",
