@@ -469,6 +469,8 @@ class Conv2dFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             if ctx.input_is_relu:
                 call("sisr_conv_dgrad_masked", d, dpre, wf, wd, dx, x, 0.0, st)
+                if len(_premasked) > 256:     # callers that never reach begin_step()
+                    _premasked.clear()
                 _premasked[dx.data_ptr()] = dx
             else:
                 call("sisr_conv_dgrad", d, dpre, wf, wd, dx, st)
@@ -601,6 +603,8 @@ class BnActFn(torch.autograd.Function):
                  slope, red, ctx.count, dy, colsum, rows, c, st)
             if colsum is not None:
                 # per-channel sum of dy = bias gradient of the producing conv; handed to its backward
+                if len(_colsum_cache) > 256:
+                    _colsum_cache.clear()
                 _colsum_cache[dy.data_ptr()] = (dy, colsum)
         dgamma = dbeta = dslope = None
         if not ctx.skip_params:
