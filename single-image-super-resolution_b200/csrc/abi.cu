@@ -234,9 +234,11 @@ static int conv_dgrad_impl(const sisr_conv_desc* d, const sisr_bf16* dy, const s
     p.GH = d->h / 2; p.GW = d->w / 2; p.trav_stride = 1;
     p.lower_w = p.lower_h = 0; p.upper_w = p.upper_h = 0;
     p.osy = p.osx = 2;
+    int nt = 0;
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
-        int nt = 0;
+        const int c = ph * 2 + pw;
+        p.cls_tap_begin[c] = nt;
         for (int kh = 0; kh < 3; ++kh) {
           if ((ph + 1 - kh) % 2) continue;
           for (int kw = 0; kw < 3; ++kw) {
@@ -247,10 +249,14 @@ static int conv_dgrad_impl(const sisr_conv_desc* d, const sisr_bf16* dy, const s
             ++nt;
           }
         }
-        p.num_taps = nt;
-        p.opy = ph; p.opx = pw;
-        if (int rc = igemm_launch(p, S(s))) return fail(rc, "conv_dgrad(s2): %s", igemm_last_error());
+        p.cls_tap_count[c] = nt - p.cls_tap_begin[c];
+        p.cls_opy[c] = ph;
+        p.cls_opx[c] = pw;
       }
+    p.num_taps = nt;          // 9 taps in 4 parity classes (1 + 2 + 2 + 4), one launch
+    p.n_classes = 4;
+    p.opy = p.opx = 0;
+    if (int rc = igemm_launch(p, S(s))) return fail(rc, "conv_dgrad(s2): %s", igemm_last_error());
     return 0;
   }
   if (d->ps_r == 2) return fail(1, "conv_dgrad: PixelShuffle layout needs a tensor-core shape");

@@ -42,6 +42,11 @@ struct IgemmProblem {
   int OH, OW, ldc;
   int osy, osx, opy, opx;
   int ps_c;
+  // optional tap classes (stride-2 dgrad: the four output parities in ONE launch): class c uses taps
+  // [cls_tap_begin[c], +cls_tap_count[c]) and writes to (gh*osy + cls_opy[c], gw*osx + cls_opx[c]);
+  // n_classes <= 1: all num_taps taps, (opy, opx)
+  int n_classes;
+  int cls_tap_begin[4], cls_tap_count[4], cls_opy[4], cls_opx[4];
   // fused epilogue
   const float* bias;       // [Cout] or nullptr (indexed by GEMM column)
   int act;                 // Act

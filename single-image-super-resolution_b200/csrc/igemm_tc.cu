@@ -51,9 +51,15 @@ struct EpiParams {
   float mask_slope;
 };
 
+struct ClassTable {
+  int n;                 // number of tap classes (>= 1)
+  int tap_begin[4], tap_count[4], opy[4], opx[4];
+};
+
 struct KParams {
   int M, GH, GW, trav_stride, lower_w, lower_h;
   int cin_blocks, num_taps, n_tiles, m_tiles;
+  ClassTable cls;
   IgemmTaps taps;
   EpiParams e;
 };
@@ -77,6 +83,7 @@ struct HParams {
 struct TParams {
   int M, GH, GW, trav_stride, lower_w, lower_h;
   int cin_blocks, num_taps, p_tiles, cout;
+  ClassTable cls;
   int flat;   // output pixel index == accumulator column index (no parity / stride remap)
   IgemmTaps taps;
   EpiParams e;
@@ -111,7 +118,8 @@ __device__ __forceinline__ float column_sums_32x32(float (&v)[32], int lane) {
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t tmem_tile, int quad, int lane,
                                               int n0, int cout, int n_img, int gh, int gw, bool valid,
-                                              float slope, const float* s_bias, float* s_stats) {
+                                              float slope, const float* s_bias, float* s_stats, int opy,
+                                              int opx) {
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     uint32_t raw[32];
@@ -133,8 +141,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t tmem_
       ox = gw * 2 + (sub & 1);
     } else {
       ch = ncol;
-      oy = gh * e.osy + e.opy;
-      ox = gw * e.osx + e.opx;
+      oy = gh * e.osy + opy;
+      ox = gw * e.osx + opx;
     }
     const size_t off = (static_cast<size_t>(n_img * e.OH + oy) * e.OW + ox) * e.ldc + ch;
     if (e.mask && valid) {   // fused activation backward of the tensor this gradient belongs to
@@ -219,8 +227,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
-  const int num_kb = p.num_taps * p.cin_blocks;
+  const int per_class = p.m_tiles * p.n_tiles;
+  const int num_tiles = per_class * p.cls.n;
   const int cout = p.n_tiles * BN;
 
   if (warp == 0 && lane == 0) {
@@ -256,15 +264,16 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int hw = p.GH * p.GW;
       uint32_t kbg = 0;   // k-block counter across tiles (pipeline stage / phase)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * kBM;
-        const int n0 = (tile % p.n_tiles) * BN;
+        const int cls = tile / per_class, t_in = tile - cls * per_class;
+        const int m0 = (t_in / p.n_tiles) * kBM;
+        const int n0 = (t_in % p.n_tiles) * BN;
         const int n_img = m0 / hw;
         const int rem = m0 - n_img * hw;
         const int gh = rem / p.GW;
         const int gw = rem - gh * p.GW;
         const int cw = gw * p.trav_stride + p.lower_w;
         const int ch = gh * p.trav_stride + p.lower_h;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
+        for (int tap = p.cls.tap_begin[cls]; tap < p.cls.tap_begin[cls] + p.cls.tap_count[cls]; ++tap) {
           for (int cb = 0; cb < p.cin_blocks; ++cb, ++kbg) {
             const uint32_t s = kbg % STAGES;
             const uint32_t round = kbg / STAGES;
@@ -286,6 +295,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t kbg = 0, it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, use = it >> 1;
+      const int num_kb = p.cls.tap_count[tile / per_class] * p.cin_blocks;
       mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1) ^ 1);   // epilogue drained this buffer
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
@@ -317,8 +327,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, use = it >> 1;
-      const int n0 = (tile % p.n_tiles) * BN;
-      const int row = (tile / p.n_tiles) * kBM + quad * 32 + lane;
+      const int cls = tile / per_class, t_in = tile - cls * per_class;
+      const int n0 = (t_in % p.n_tiles) * BN;
+      const int row = (t_in / p.n_tiles) * kBM + quad * 32 + lane;
       const bool valid = row < p.M;
       const int rr = valid ? row : 0;
       const int n_img = rr / hw;
@@ -328,7 +339,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
       tc_fence_after();
       epilogue_tile<BN>(p.e, tmem_base + acc * BN, quad, lane, n0, cout, n_img, gh, gw, valid, slope,
-                        s_bias, s_stats);
+                        s_bias, s_stats, p.cls.opy[cls], p.cls.opx[cls]);
       // this warp's TMEM reads of the buffer are complete: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -369,7 +380,7 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = p.num_taps * p.cin_blocks;
+  const int num_tiles = p.p_tiles * p.cls.n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_px);
@@ -398,15 +409,16 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
     if (lane == 0) {
       const int hw = p.GH * p.GW;
       uint32_t kbg = 0;
-      for (int tile = blockIdx.x; tile < p.p_tiles; tile += gridDim.x) {
-        const int m0 = tile * kTP;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int cls = tile / p.p_tiles;
+        const int m0 = (tile - cls * p.p_tiles) * kTP;
         const int n_img = m0 / hw;
         const int rem = m0 - n_img * hw;
         const int gh = rem / p.GW;
         const int gw = rem - gh * p.GW;
         const int cw = gw * p.trav_stride + p.lower_w;
         const int ch = gh * p.trav_stride + p.lower_h;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
+        for (int tap = p.cls.tap_begin[cls]; tap < p.cls.tap_begin[cls] + p.cls.tap_count[cls]; ++tap) {
           for (int cb = 0; cb < p.cin_blocks; ++cb, ++kbg) {
             const uint32_t s = kbg % STAGES;
             mbar_wait(smem_u32(&empty_bar[s]), ((kbg / STAGES) & 1) ^ 1);
@@ -424,8 +436,9 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
     // ------------------------------------------------------------ MMA issuer: D[co, px] += W * X^T
     constexpr uint32_t idesc = umma_idesc_bf16(128, kTP, 0, 0);
     uint32_t kbg = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.p_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, use = it >> 1;
+      const int num_kb = p.cls.tap_count[tile / p.p_tiles] * p.cin_blocks;
       mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1) ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * kTP;
@@ -471,12 +484,13 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
       for (int i = threadIdx.x - 64; i < 2 * 128; i += 256) s_sum[i] = 0.f;
     float s1 = 0.f, s2 = 0.f;   // BN statistics of this channel over this warp's chunks
     uint32_t it = 0, chunk_no = 0;
-    for (int tile = blockIdx.x; tile < p.p_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, use = it >> 1;
+      const int cls = tile / p.p_tiles;
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
       tc_fence_after();
       if (warp_active) {
-        const int m0 = tile * kTP;
+        const int m0 = (tile - cls * p.p_tiles) * kTP;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kTP;
         uint32_t raw[32];
         tmem_ld_32x32(trow + half * 32, raw);
@@ -522,7 +536,8 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
                 const int rem = px - n_img * hw;
                 const int gh = rem / p.GW;
                 const int gw = rem - gh * p.GW;
-                opix = static_cast<size_t>(n_img * e.OH + gh * e.osy + e.opy) * e.OW + gw * e.osx + e.opx;
+                opix = static_cast<size_t>(n_img * e.OH + gh * e.osy + p.cls.opy[cls]) * e.OW + gw * e.osx +
+                       p.cls.opx[cls];
               }
               uint4 val = *reinterpret_cast<const uint4*>(stage + row * row_words + seg * 4);
               if (e.mask) {
@@ -728,7 +743,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
       tc_fence_after();
       epilogue_tile<BN>(p.e, tmem_base + acc * BN, quad, lane, n0, cout, n_img, gh, gw, valid, slope,
-                        s_bias, s_stats);
+                        s_bias, s_stats, p.e.opy, p.e.opx);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
@@ -817,7 +832,7 @@ Plan make_plan(const IgemmProblem& p) {
   const int cin_blocks = p.Cin / kBK;
   const int cands[3] = {256, 128, 64};
   // halo geometry
-  bool halo_ok = g_halo_mode > 0 && p.trav_stride == 1 && p.GH == p.H && p.GW == p.W && p.num_taps == 9 &&
+  bool halo_ok = g_halo_mode > 0 && p.n_classes <= 1 && p.trav_stride == 1 && p.GH == p.H && p.GW == p.W && p.num_taps == 9 &&
                  p.lower_w == -1 && p.lower_h == -1;
   for (int t = 0; halo_ok && t < 9; ++t) halo_ok = p.taps.off_w[t] <= 2 && p.taps.off_h[t] <= 2;
   int tw = 0, r = 0, tiles_w = 0, tiles_h = 0;
@@ -859,6 +874,21 @@ Plan make_plan(const IgemmProblem& p) {
   return best;
 }
 
+void fill_classes(ClassTable& c, const IgemmProblem& p) {
+  if (p.n_classes > 1) {
+    c.n = p.n_classes;
+    for (int i = 0; i < 4; ++i) {
+      c.tap_begin[i] = p.cls_tap_begin[i]; c.tap_count[i] = p.cls_tap_count[i];
+      c.opy[i] = p.cls_opy[i]; c.opx[i] = p.cls_opx[i];
+    }
+  } else {
+    c.n = 1;
+    for (int i = 0; i < 4; ++i) {
+      c.tap_begin[i] = 0; c.tap_count[i] = p.num_taps; c.opy[i] = p.opy; c.opx[i] = p.opx;
+    }
+  }
+}
+
 void fill_epi(EpiParams& e, const IgemmProblem& p) {
   e.out = p.out;
   e.OH = p.OH; e.OW = p.OW; e.ldc = p.ldc;
@@ -880,6 +910,7 @@ bool igemm_supported(const IgemmProblem& p) {
   if (p.Cin % 64 || p.Cout % 64 || p.Cout > kMaxCout) return false;
   if (p.stats && p.stats_rows < num_sms()) return false;
   if (p.num_taps < 1 || p.num_taps > kMaxTaps) return false;
+  if (p.n_classes > 4 || (p.n_classes > 1 && p.stats)) return false;
   if (p.ldc % 8) return false;
   if (p.ps_c > 0 && (p.ps_c % 32)) return false;
   if ((reinterpret_cast<uintptr_t>(p.x) & 15) || (reinterpret_cast<uintptr_t>(p.w) & 15) ||
@@ -896,7 +927,7 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     return 1;
   }
   const bool flat_out = p.osy == 1 && p.osx == 1 && p.opy == 0 && p.opx == 0 && p.OH == p.GH && p.OW == p.GW;
-  if (g_transposed && p.Cout <= 128 && p.ps_c == 0 && flat_out && g_halo_mode != 2) {
+  if (g_transposed && p.Cout <= 128 && p.ps_c == 0 && flat_out && p.n_classes <= 1 && g_halo_mode != 2) {
     CUtensorMap tpx, tw;
     if (make_tmap_2d_bf16(&tw, p.w, p.Cout, p.Ktot, p.Ktot, kBK, 128)) {
       snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
@@ -917,9 +948,12 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     tp.p_tiles = static_cast<int>((Mt + kTP - 1) / kTP);
     tp.cout = p.Cout;
     tp.taps = p.taps;
+    fill_classes(tp.cls, p);
     fill_epi(tp.e, p);
-    tp.flat = (p.osy == 1 && p.osx == 1 && p.opy == 0 && p.opx == 0 && p.OH == p.GH && p.OW == p.GW) ? 1 : 0;
-    const int grid = tp.p_tiles < num_sms() ? tp.p_tiles : num_sms();
+    tp.flat = (p.n_classes <= 1 && p.osy == 1 && p.osx == 1 && p.opy == 0 && p.opx == 0 && p.OH == p.GH &&
+               p.OW == p.GW) ? 1 : 0;
+    const int t_tiles = tp.p_tiles * tp.cls.n;
+    const int grid = t_tiles < num_sms() ? t_tiles : num_sms();
     static bool configured = false;
     return launch_kernel(igemm_t_kernel<4>, &configured, 4 * kTStage + 1024, tpx, tw, tp, grid, stream,
                          kTThreads);
@@ -983,8 +1017,9 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   kp.n_tiles = p.Cout / bn;
   kp.m_tiles = static_cast<int>((M + kBM - 1) / kBM);
   kp.taps = p.taps;
+  fill_classes(kp.cls, p);
   fill_epi(kp.e, p);
-  const int tiles = kp.m_tiles * kp.n_tiles;
+  const int tiles = kp.m_tiles * kp.n_tiles * kp.cls.n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   switch (bn) {
     case 64:
