@@ -4,6 +4,7 @@
 #include "optim.h"
 
 #include <math.h>
+#include <stdint.h>
 
 namespace sisr {
 
@@ -38,15 +39,31 @@ __global__ void adam_multi_kernel(AdamTable tab, const float* __restrict__ hyper
   const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2];
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * grad_scale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= grad_scale;
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  };
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                     reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = tid; i < n4; i += nthreads) {       // 16-byte accesses on the bulk of the tensor
+    float4 p4 = reinterpret_cast<float4*>(p)[i];
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 m4 = reinterpret_cast<float4*>(m)[i];
+    float4 v4 = reinterpret_cast<float4*>(v)[i];
+    upd(p4.x, g4.x, m4.x, v4.x);
+    upd(p4.y, g4.y, m4.y, v4.y);
+    upd(p4.z, g4.z, m4.z, v4.z);
+    upd(p4.w, g4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(p)[i] = p4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
   }
+  for (long long i = n4 * 4 + tid; i < n; i += nthreads) upd(p[i], g[i], m[i], v[i]);
 }
 
 }  // namespace
@@ -71,8 +88,8 @@ int adam_multi(int n, float* const* p, const float* const* g, float* const* m, f
       tab.numel[i] = numel[base + i];
       if (numel[base + i] > biggest) biggest = numel[base + i];
     }
-    long long bx = (biggest + 256 * 4 - 1) / (256 * 4);
-    if (bx > 148 * 4) bx = 148 * 4;
+    long long bx = (biggest + 256 * 8 - 1) / (256 * 8);
+    if (bx > 148 * 8) bx = 148 * 8;
     dim3 grid(static_cast<unsigned>(bx), cnt);
     adam_multi_kernel<<<grid, 256, 0, s>>>(tab, hyper, b1, b2, eps, grad_scale);
   }
