@@ -307,7 +307,6 @@ def run_ours(args):
     import torch.distributed as dist
     import sisr_b200 as m  # noqa: F401
     from sisr_b200 import _lib, parallel
-    from oracle import state_factory as S   # synthetic patch recipe only (host side)
 
     rank, local, world = parallel.init_distributed()
     sampler = ClockSampler(local)
@@ -322,7 +321,8 @@ def run_ours(args):
         from sisr_b200 import ops as _ops
         _ops.set_sync_group(None)
     tr = build_trainer(dev, batch, world, gs)
-    hr_host = S.synthetic_hr(1234 + rank, batch, 96).pin_memory()
+    gen = torch.Generator().manual_seed(1234 + rank)          # synthetic HR patches ~ U[-1, 1]
+    hr_host = (torch.rand((batch, 3, 96, 96), generator=gen) * 2 - 1).pin_memory()
     import torch.nn.functional as F
     lr_host = F.interpolate(hr_host, (24, 24), mode="bicubic", align_corners=True).clamp(-1, 1).pin_memory()
     hr, lr = hr_host.to(dev), lr_host.to(dev)
