@@ -154,24 +154,32 @@ __device__ __forceinline__ int find_layer(const int* __restrict__ begin, int n, 
   return lo;
 }
 
-// t[k] = sum_co W[co,k] u[co] for a 128-column chunk of one layer (training layers only)
+// t[k] = sum_co W[co,k] u[co] for a 32-column chunk of one layer (training layers only): 8 row groups
+// per block keep the serial depth at cout/8 loads per thread
+constexpr int kWtuCols = 32;
 __global__ void __launch_bounds__(256)
 sn_batched_wtu_kernel(const __grid_constant__ SnTable tab) {
-  __shared__ float part[128];
+  __shared__ float part[8][kWtuCols];
   const int* blk_begin = tab.wtu_begin;
   const int l = find_layer(blk_begin, tab.n, blockIdx.x);
   const SnLayer& L = tab.L[l];
   if (!L.training) return;
-  const int k = (blockIdx.x - blk_begin[l]) * 128 + (threadIdx.x & 127);
-  const int half = threadIdx.x >> 7;
+  const int col = threadIdx.x & (kWtuCols - 1), grp = threadIdx.x / kWtuCols;
+  const int k = (blockIdx.x - blk_begin[l]) * kWtuCols + col;
   float acc = 0.f;
   if (k < L.K) {
-    const int c0 = half ? L.cout / 2 : 0, c1 = half ? L.cout : L.cout / 2;
+    const int per = (L.cout + 7) / 8;
+    const int c0 = grp * per, c1 = min(L.cout, c0 + per);
+#pragma unroll 8
     for (int co = c0; co < c1; ++co) acc = fmaf(L.w[static_cast<size_t>(co) * L.K + k], L.u[co], acc);
   }
-  if (half) part[threadIdx.x & 127] = acc;
+  part[grp][col] = acc;
   __syncthreads();
-  if (!half && k < L.K) L.t[k] = acc + part[threadIdx.x];
+  if (grp == 0 && k < L.K) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) acc += part[g][col];
+    L.t[k] = acc;
+  }
 }
 // s_raw[co] = sum_k W[co,k] * (training ? t[k] : v[k]); one block per (layer, row)
 __global__ void __launch_bounds__(128)
@@ -227,16 +235,54 @@ sn_batched_finish_kernel(const __grid_constant__ SnTable tab, float eps) {
   }
 }
 
-// weight_prep for every conv of a network; block -> (layer, chunk of 1024 elements)
+// weight_prep for every conv of a network.  Layers with 3x3 taps and channel counts that are multiples
+// of 64 are processed as (16 co') x (64 ci) x 9 slabs through shared memory, so that the fp32 master
+// rows are read, and both bf16 layouts written, in full 128-byte lines; the other (3-channel) layers
+// use one thread per element.  block -> (layer, slab | chunk of 1024 elements)
+constexpr int kPrepCo = 16;   // rows (co') per slab
+__device__ __forceinline__ bool prep_tiled(const PrepLayer& L) {
+  return L.k == 3 && L.cin % 64 == 0 && L.cout % 64 == 0;
+}
 __global__ void __launch_bounds__(256)
 weight_prep_batched_kernel(const __grid_constant__ PrepTable tab) {
+  extern __shared__ __align__(16) uint8_t prep_smem[];
   const int* blk_begin = tab.blk_begin;
   const int l = find_layer(blk_begin, tab.n, blockIdx.x);
   const PrepLayer& L = tab.L[l];
   const float inv = L.sigma ? 1.f / *L.sigma : 1.f;
   const int taps = L.k * L.k;
+  const int unit = blockIdx.x - blk_begin[l];
+  if (prep_tiled(L)) {
+    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(prep_smem);   // [kPrepCo co'][64 ci][9] (+pad)
+    constexpr int kRow = 64 * 9 + 2;
+    const int cib = unit % (L.cin / 64), cob = unit / (L.cin / 64);      // cob: block of kPrepCo rows
+    for (int i = threadIdx.x; i < kPrepCo * 576; i += blockDim.x) {
+      const int r = i / 576, j = i - r * 576;                           // j = ci_local * 9 + tap
+      const int co = unpermute_row(cob * kPrepCo + r, L.cout, L.ps_r);
+      tile[r * kRow + j] =
+          __float2bfloat16_rn(L.w[(static_cast<size_t>(co) * L.cin + cib * 64) * 9 + j] * inv);
+    }
+    __syncthreads();
+    // wf[co'][tap][ci]: rows of 64 ci (128 B)
+    for (int i = threadIdx.x; i < kPrepCo * 576; i += blockDim.x) {
+      const int ci = i & 63, tap = (i >> 6) % 9, r = i / 576;
+      L.wf[(static_cast<size_t>(cob * kPrepCo + r) * 9 + tap) * L.cin + cib * 64 + ci] =
+          tile[r * kRow + ci * 9 + tap];
+    }
+    // wd[ci][tap][co']: runs of kPrepCo co' (32 B)
+    if (L.wd)
+      for (int i = threadIdx.x; i < kPrepCo * 576; i += blockDim.x) {
+        const int r = i % kPrepCo, tap = (i / kPrepCo) % 9, ci = i / (kPrepCo * 9);
+        L.wd[(static_cast<size_t>(cib * 64 + ci) * 9 + tap) * L.cout + cob * kPrepCo + r] =
+            tile[r * kRow + ci * 9 + tap];
+      }
+    if (L.bias_perm && cib == 0)
+      for (int r = threadIdx.x; r < kPrepCo; r += blockDim.x)
+        L.bias_perm[cob * kPrepCo + r] = L.bias[unpermute_row(cob * kPrepCo + r, L.cout, L.ps_r)];
+    return;
+  }
   const long long total = static_cast<long long>(L.cout) * taps * L.cin;
-  const long long base = static_cast<long long>(blockIdx.x - blk_begin[l]) * 1024;
+  const long long base = static_cast<long long>(unit) * 1024;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const long long i = base + j * 256 + threadIdx.x;
@@ -458,7 +504,7 @@ int sn_power_iteration_batched(const SnLayer* layers, int n_layers, float eps, c
       tab.L[i] = layers[base + i];
       tab.wtu_begin[i] = wtu;
       tab.row_begin[i] = rows;
-      if (tab.L[i].training) wtu += (tab.L[i].K + 127) / 128;
+      if (tab.L[i].training) wtu += (tab.L[i].K + kWtuCols - 1) / kWtuCols;
       rows += tab.L[i].cout;
     }
     tab.wtu_begin[tab.n] = wtu;
@@ -479,11 +525,23 @@ int weight_prep_batched(const PrepLayer* layers, int n_layers, cudaStream_t s) {
       tab.L[i] = layers[base + i];
       if (tab.L[i].ps_r > 1 && tab.L[i].cout % (tab.L[i].ps_r * tab.L[i].ps_r)) return 1;
       tab.blk_begin[i] = blocks;
-      const long long total = static_cast<long long>(tab.L[i].cout) * tab.L[i].cin * tab.L[i].k * tab.L[i].k;
-      blocks += static_cast<int>((total + 1023) / 1024);
+      const PrepLayer& Li = tab.L[i];
+      const long long total = static_cast<long long>(Li.cout) * Li.cin * Li.k * Li.k;
+      if (Li.k == 3 && Li.cin % 64 == 0 && Li.cout % 64 == 0)
+        blocks += (Li.cout / kPrepCo) * (Li.cin / 64);
+      else
+        blocks += static_cast<int>((total + 1023) / 1024);
     }
     tab.blk_begin[tab.n] = blocks;
-    if (blocks > 0) weight_prep_batched_kernel<<<blocks, 256, 0, s>>>(tab);
+    constexpr int kPrepSmem = kPrepCo * (64 * 9 + 2) * 2;
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(weight_prep_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kPrepSmem) != cudaSuccess)
+        return 3;
+      configured = true;
+    }
+    if (blocks > 0) weight_prep_batched_kernel<<<blocks, 256, kPrepSmem, s>>>(tab);
   }
   return check();
 }
