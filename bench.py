@@ -316,7 +316,9 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     batch = args.batch
     use_graph = not args.no_graph      # NCCL all-reduces and the peer-memory SyncBN kernels are captured too
-    gs = parallel.GradSync() if (world > 1 and not os.environ.get("SISR_DIAG_NO_GRADSYNC")) else None
+    bucket = int(os.environ.get("SISR_BUCKET_MB", "0")) << 20
+    gs = (parallel.GradSync(bucket_bytes=bucket) if bucket else parallel.GradSync()) \
+        if (world > 1 and not os.environ.get("SISR_DIAG_NO_GRADSYNC")) else None
     if os.environ.get("SISR_DIAG_NO_SYNCBN"):      # attribution experiments only (results differ from the spec)
         from sisr_b200 import ops as _ops
         _ops.set_sync_group(None)
