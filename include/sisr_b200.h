@@ -181,6 +181,12 @@ int sisr_dhead_backward(const sisr_bf16* x_flat, const float* w0, const float* w
                         float* dw2, float* db2, float* dx_flat, int batch, int fc_in, int fc_mid,
                         int need_wgrad, void* stream);
 
+/* ---- stand-alone nn.PixelShuffle(2) on NHWC bf16 (model_generator_progressive.py:54, the 64->16->4
+ *      channel stages whose convs are too narrow for the fused store): inverse = 0: x [n,h,w,4*c_out]
+ *      -> y [n,2h,2w,c_out]; inverse = 1: x is the gradient [n,2h,2w,c_out], y receives [n,h,w,4*c_out] ---- */
+int sisr_pixel_shuffle2(const sisr_bf16* x, sisr_bf16* y, int n, int h, int w, int c_out, int inverse,
+                        void* stream);
+
 /* ---- LR synthesis: utils.lr_from_hr (utils.py:16-31) = F.interpolate(bicubic, align_corners=True) +
  *      clamp to [-1,1]; NCHW fp32.  The backward (content_loss_on_lr mode, train.py:95-97) passes the
  *      gradient where the interpolated value stayed inside (-1, 1). ---- */

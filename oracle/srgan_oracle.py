@@ -266,6 +266,44 @@ def generator_forward(st: State, x: torch.Tensor, training: bool = True,
     return torch.tanh(_qg(conv(st, _end_prefix(st), x, 1, 1, training)))
 
 
+# --------------------------------------------------------------------------- older progressive design
+def _progressive_base(st: State, x: torch.Tensor, p: str, training: bool) -> torch.Tensor:
+    """model_generator_progressive.py:21-44 (GeneratorProgresiveBase: no spectral norm, no global skip)."""
+    x = _qg(conv(st, p + "first_layers.0.", _q(x), 1, 4, training))
+    x = _q(prelu(st, p + "first_layers.1.", x))
+    n_blocks = _count(st, p + "block_list.{}.layers.0.bias")
+    for i in range(n_blocks):
+        q = f"{p}block_list.{i}.layers."
+        y = _q(conv(st, q + "0.", x, 1, 1, training))
+        y = batch_norm(st, q + "1.", y, training)
+        y = _q(prelu(st, q + "2.", y))
+        y = _q(conv(st, q + "3.", y, 1, 1, training))
+        y = batch_norm(st, q + "4.", y, training)
+        x = _q(x + y)
+    x = _q(conv(st, p + "block_list_end.0.", x, 1, 1, training))
+    return _q(batch_norm(st, p + "block_list_end.1.", x, training))
+
+
+def progressive_forward_no_end(st: State, x: torch.Tensor, p: str = "beginning.",
+                               training: bool = True) -> torch.Tensor:
+    """model_generator_progressive.py:52-56: ``beginning`` = Sequential[prefix, conv3x3 nf->nf,
+    PixelShuffle(2), PReLU]; the prefix (index 0) is the base network or the ``beginning`` of the
+    previous stage (a Sequential again), which is read off the key layout."""
+    if (p + "0.first_layers.0.weight") in st:
+        x = _progressive_base(st, x, p + "0.", training)
+    else:
+        x = progressive_forward_no_end(st, x, p + "0.", training)
+    x = _qg(conv(st, p + "1.", x, 1, 1, training))
+    x = pixel_shuffle(x, 2)
+    return _q(prelu(st, p + "3.", x))
+
+
+def progressive_forward(st: State, x: torch.Tensor, training: bool = True) -> torch.Tensor:
+    """model_generator_progressive.py:61-64: beginning, then end = conv3x3 (nf/4 -> 3) + Tanh."""
+    x = progressive_forward_no_end(st, x, "beginning.", training)
+    return torch.tanh(_qg(conv(st, "end.0.", x, 1, 1, training)))
+
+
 # --------------------------------------------------------------------------- discriminator
 def discriminator_forward(st: State, x: torch.Tensor, strides: Sequence[int],
                           training: bool = True) -> torch.Tensor:

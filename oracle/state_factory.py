@@ -88,6 +88,33 @@ def generator_state(seed: int, n_blocks: int = 16, nf: int = 64, nf_last: int = 
     return st
 
 
+def progressive_state(seed: int, n_blocks: int = 2, nf: int = 64, n_suffix: int = 1, in_ch: int = 3) -> State:
+    """Keys of model_generator_progressive.GeneratorSuffix chained ``n_suffix`` times over a
+    GeneratorProgresiveBase (each stage wraps the previous stage's ``beginning``; channels shrink x1/4)."""
+    rng = _Rng(seed)
+    st: State = {}
+    p = "beginning." + "0." * n_suffix               # the base network sits n_suffix Sequentials deep
+    _conv(st, p + "first_layers.0.", rng, in_ch, nf, 9, False)
+    _prelu(st, p + "first_layers.1.")
+    for i in range(n_blocks):
+        q = f"{p}block_list.{i}.layers."
+        _conv(st, q + "0.", rng, nf, nf, 3, False)
+        _bn(st, q + "1.", rng, nf)
+        _prelu(st, q + "2.")
+        _conv(st, q + "3.", rng, nf, nf, 3, False)
+        _bn(st, q + "4.", rng, nf)
+    _conv(st, p + "block_list_end.0.", rng, nf, nf, 3, False)
+    _bn(st, p + "block_list_end.1.", rng, nf)
+    c = nf
+    for j in range(1, n_suffix + 1):                   # stage j (1 = innermost): conv c->c, shuffle to c/4
+        q = "beginning." + "0." * (n_suffix - j)
+        _conv(st, q + "1.", rng, c, c, 3, False)
+        _prelu(st, q + "3.")
+        c //= 4
+    _conv(st, "end.0.", rng, c, in_ch, 3, False)
+    return st
+
+
 def discriminator_state(seed: int, input_shape=(3, 96, 96),
                         features: Sequence[int] = (64, 64, 128, 128, 256, 256, 512, 512),
                         strides: Sequence[int] = (1, 2, 1, 2, 1, 2, 1, 2)) -> State:

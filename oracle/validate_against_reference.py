@@ -258,6 +258,50 @@ def case_lr_from_hr(seed, gold):
     gold["lr_from_hr"] = {"seed": seed, "hr": hr, "lr": want}
 
 
+def case_progressive(n_suffix, seed, gold):
+    """model_generator_progressive.py (older design, not imported by config/train): forward, all
+    parameter gradients and the eval-mode forward of the chained GeneratorSuffix stages."""
+    import model_generator_progressive as mp
+    name = f"progressive_suffix{n_suffix}"
+    print(name)
+    st = S.progressive_state(seed, n_blocks=2, nf=64, n_suffix=n_suffix)
+    net = mp.GeneratorSuffix(mp.GeneratorProgresiveBase(2, 64), 64)
+    nf = 16
+    for _ in range(n_suffix - 1):
+        net = mp.GeneratorSuffix(net.beginning, nf)
+        nf //= 4
+    torch.nn.Module.load_state_dict(net, S.clone_state(st), strict=True)
+    x = S.synthetic_hr(seed + 1, 2, 8)
+    side = 8 * 2 ** n_suffix
+    gy = torch.randn(2, 3, side, side, generator=torch.Generator().manual_seed(seed + 2))
+    net.train()
+    y = net(x)
+    (y * gy).sum().backward()
+    ref_grads = _grads(net)
+    ref_sd = {k: v.clone() for k, v in net.state_dict().items()}
+    mine = S.clone_state(st)
+    names = O.trainable_names(mine)
+    leaf = O._leaf(mine, names)
+    y2 = O.progressive_forward(leaf, x, training=True)
+    g2 = torch.autograd.grad((y2 * gy).sum(), [leaf[k] for k in names])
+    _check("forward", y2, y)
+    floor = 1e-3 * max(float(v.norm()) for v in ref_grads.values())
+    for k, g in zip(names, g2):
+        _check("grad " + k, g, ref_grads[k], tol=1e-4, floor=floor)
+    for k in mine:
+        if k.endswith(("running_mean", "running_var")):
+            _check("buffer " + k, mine[k], ref_sd[k])
+    net.eval()
+    with torch.no_grad():
+        ye = net(x)
+    _check("eval forward", O.progressive_forward(mine, x, training=False), ye)
+    gold[name] = {"seed": seed, "n_suffix": n_suffix, "x": x, "gy": gy, "y": y.detach(), "y_eval": ye,
+                  "grad_norms": {k: float(v.norm()) for k, v in ref_grads.items()},
+                  "grads": {k: ref_grads[k] for k in names if ref_grads[k].numel() <= 40000 and
+                            ("block_list.1." in k or "first_layers" in k or "beginning.1" in k
+                             or "beginning.3" in k or "end" in k)}}
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -271,6 +315,8 @@ def main():
     case_vgg(mc, 0b10000, 310, 32, gold)
     case_vgg(mc, 0b01111, 320, 16, gold)
     case_lr_from_hr(400, gold)
+    case_progressive(1, 600, gold)
+    case_progressive(2, 610, gold)
     case_train_step(mg, md, mc, 500, gold, n_steps=1)
     case_train_step(mg, md, mc, 500, gold, n_steps=2)
     os.makedirs(GOLD, exist_ok=True)

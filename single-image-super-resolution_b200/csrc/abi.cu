@@ -437,6 +437,13 @@ int sisr_dhead_backward(const sisr_bf16* x_flat, const float* w0, const float* w
               "dhead_backward");
 }
 
+// ------------------------------------------------------------------ stand-alone PixelShuffle(2)
+int sisr_pixel_shuffle2(const sisr_bf16* x, sisr_bf16* y, int n, int h, int w, int c_out, int inverse,
+                        void* s) {
+  if (!x || !y) return fail(1, "pixel_shuffle2: null argument");
+  return wrap(pixel_shuffle2(B(x), B(y), n, h, w, c_out, inverse, S(s)), "pixel_shuffle2");
+}
+
 // ------------------------------------------------------------------ LR synthesis
 int sisr_lr_from_hr(const float* hr, float* lr, int n, int c, int h, int w, int oh, int ow, void* s) {
   if (!hr || !lr) return fail(1, "lr_from_hr: null argument");

@@ -559,6 +559,29 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x,
   }
 }
 
+// ------------------------------------------------------------------ stand-alone PixelShuffle(2)
+// NHWC bf16: x [N, H, W, 4*C] -> y [N, 2H, 2W, C] with y[n, 2h+i, 2w+j, c] = x[n, h, w, c*4 + i*2 + j]
+// (nn.PixelShuffle channel order).  inverse = 1: the same mapping read backwards (gradient).  Used by
+// the narrow-channel stages of model_generator_progressive.py; the main generator folds the shuffle
+// into the producing conv's store addressing instead.
+__global__ void pixel_shuffle2_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                      int N, int H, int W, int C, int inverse) {
+  const long long total = static_cast<long long>(N) * H * W * 4 * C;
+  for (long long o = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; o < total;
+       o += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // o indexes the shuffled tensor [N, 2H, 2W, C]
+    const int c = static_cast<int>(o % C);
+    long long q = o / C;
+    const int ox = static_cast<int>(q % (2 * W));
+    q /= 2 * W;
+    const int oy = static_cast<int>(q % (2 * H));
+    const int n = static_cast<int>(q / (2 * H));
+    const long long i = ((static_cast<long long>(n) * H + (oy >> 1)) * W + (ox >> 1)) * 4 * C + c * 4 +
+                        (oy & 1) * 2 + (ox & 1);
+    if (inverse) dst[i] = src[o]; else dst[o] = src[i];
+  }
+}
+
 // ------------------------------------------------------------------ LR synthesis (utils.py:16-31)
 // F.interpolate(mode='bicubic', align_corners=True) (cubic convolution, A = -0.75, border-clamped
 // taps) followed by the clamp to [-1, 1]; NCHW fp32 in and out.
@@ -801,6 +824,13 @@ int maxpool2_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16*
   if (C % 8 || H % 2 || W % 2) return 1;
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   maxpool2_bwd_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(x, dy, dx, N, H, W, C);
+  return check();
+}
+int pixel_shuffle2(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int H, int W, int C, int inverse,
+                   cudaStream_t s) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return 1;
+  const long long total = static_cast<long long>(N) * H * W * 4 * C;
+  pixel_shuffle2_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(src, dst, N, H, W, C, inverse);
   return check();
 }
 int lr_from_hr(const float* hr, float* lr, const float* dlr, float* dhr, int N, int C, int H, int W, int OH,

@@ -38,6 +38,9 @@ int act_bwd(const __nv_bfloat16* dout, const __nv_bfloat16* out, int act, float 
 int maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int N, int H, int W, int C, cudaStream_t s);
 int maxpool2_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16* dx, int N, int H,
                  int W, int C, cudaStream_t s);
+// PixelShuffle(2) on NHWC bf16: [N,H,W,4C] -> [N,2H,2W,C] (inverse = 1: the gradient mapping)
+int pixel_shuffle2(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int H, int W, int C, int inverse,
+                   cudaStream_t s);
 // lr = clamp(bicubic(hr)) (dlr == nullptr) or its backward dhr (dlr != nullptr)
 int lr_from_hr(const float* hr, float* lr, const float* dlr, float* dhr, int N, int C, int H, int W, int OH,
                int OW, cudaStream_t s);

@@ -729,6 +729,29 @@ class MSEFn(torch.autograd.Function):
         return ga, gb
 
 
+class PixelShuffle2Fn(torch.autograd.Function):
+    """nn.PixelShuffle(2) on NHWC bf16: [N,H,W,4C] -> [N,2H,2W,C] (stand-alone kernel)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x, "PixelShuffle2Fn")
+        x = x.contiguous()
+        n, h, w, c4 = x.shape
+        if c4 % 4:
+            raise _lib.SisrError("PixelShuffle(2) needs a channel count divisible by 4")
+        y = torch.empty((n, 2 * h, 2 * w, c4 // 4), dtype=x.dtype, device=x.device)
+        call("sisr_pixel_shuffle2", x, y, n, h, w, c4 // 4, 0, _stream())
+        ctx.shape = (n, h, w, c4)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, h, w, c4 = ctx.shape
+        gx = torch.empty((n, h, w, c4), dtype=gy.dtype, device=gy.device)
+        call("sisr_pixel_shuffle2", gy.contiguous(), gx, n, h, w, c4 // 4, 1, _stream())
+        return gx
+
+
 class LrFromHrFn(torch.autograd.Function):
     """utils.lr_from_hr: bicubic (align_corners=True) down-sampling + clamp to [-1, 1], NCHW fp32."""
 

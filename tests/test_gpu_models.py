@@ -99,6 +99,52 @@ def test_generator_vs_reference_golden(cuda, golden_dir, n_suffix):
     assert O.psnr(ye.cpu(), g["y_eval"]) >= 50.0
 
 
+@pytest.mark.parametrize("n_suffix", [1, 2])
+def test_progressive_generator_vs_reference_golden(cuda, golden_dir, n_suffix):
+    """model_generator_progressive.py drop-in (GeneratorProgresiveBase + chained GeneratorSuffix stages,
+    64 -> 16 channels) against the real reference's outputs and gradients."""
+    from sisr_b200 import model_generator_progressive as mp
+    g = _load(golden_dir, f"progressive_suffix{n_suffix}")
+    st = S.progressive_state(g["seed"], n_blocks=2, nf=64, n_suffix=n_suffix)
+    net = mp.GeneratorSuffix(mp.GeneratorProgresiveBase(2, 64), 64)
+    nf = 16
+    for _ in range(n_suffix - 1):
+        net = mp.GeneratorSuffix(net.beginning, nf)
+        nf //= 4
+    assert set(net.state_dict()) == set(st)
+    torch.nn.Module.load_state_dict(net, S.clone_state(st), strict=True)
+    net = net.cuda().train()
+    y = net(g["x"].cuda())
+    assert y.shape == g["y"].shape and y.dtype == torch.float32
+    assert rel(y, g["y"]) < 1e-2
+    (y * g["gy"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in net.named_parameters()}
+    top = max(g["grad_norms"].values())
+    for k, ref in g["grads"].items():
+        if g["grad_norms"][k] > 1e-2 * top:
+            assert cos(grads[k], ref) > 0.85, k
+    for k, n_ref in g["grad_norms"].items():
+        if n_ref > 1e-2 * top:
+            assert abs(float(grads[k].norm()) - n_ref) < 0.15 * n_ref, k
+    emu = S.progressive_state(g["seed"], n_blocks=2, nf=64, n_suffix=n_suffix)
+    names = O.trainable_names(emu)
+    leaf = O._leaf(emu, names)
+    with O.emulate_bf16_storage():
+        y_emu = O.progressive_forward(leaf, g["x"], training=True)
+        g_emu = dict(zip(names, torch.autograd.grad((y_emu * g["gy"]).sum(), [leaf[k] for k in names])))
+    assert rel(y, y_emu) < 1e-2
+    top_e = max(float(v.norm()) for v in g_emu.values())
+    for k, r in g_emu.items():
+        if float(r.norm()) > 1e-2 * top_e:
+            assert rel(grads[k], r) < 8e-2, k
+    net.eval()
+    with torch.no_grad():
+        ye = net(g["x"].cuda())
+    assert rel(ye, g["y_eval"]) < 1e-2
+    with pytest.raises(NotImplementedError):
+        mp.GeneratorSuffix(net.beginning, 4)
+
+
 def test_discriminator_vs_reference_golden(cuda, golden_dir):
     import sisr_b200 as m
     g = _load(golden_dir, "discriminator")

@@ -311,3 +311,20 @@ def test_lr_from_hr_matches_reference_and_torch(cuda, golden_dir):
     hr_d = hr.cuda().requires_grad_(True)
     lr_from_hr(hr_d, (24, 24)).backward(gy.cuda())
     assert rel(hr_d.grad, hr_r.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 5, 7), (3, 64, 8, 8), (1, 256, 4, 6)])
+def test_pixel_shuffle2_standalone_bit_exact(cuda, shape):
+    """sisr_pixel_shuffle2 (model_generator_progressive.py:54): a permutation, so bit-exact against
+    F.pixel_shuffle both ways."""
+    from sisr_b200 import ops
+    n, c4, h, w = shape
+    gen = torch.Generator().manual_seed(zlib.crc32(repr(shape).encode()))
+    x = bf(torch.randn(n, c4, h, w, generator=gen))
+    xd = nhwc(x).requires_grad_(True)
+    y = ops.PixelShuffle2Fn.apply(xd)
+    assert y.shape == (n, 2 * h, 2 * w, c4 // 4)
+    assert torch.equal(nchw(y.detach()), F.pixel_shuffle(x, 2))
+    gy = bf(torch.randn(n, c4 // 4, 2 * h, 2 * w, generator=gen))
+    y.backward(nhwc(gy))
+    assert torch.equal(nchw(xd.grad), F.pixel_unshuffle(gy, 2))

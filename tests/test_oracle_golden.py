@@ -29,6 +29,23 @@ def test_generator_matches_reference(golden_dir, n_suffix):
     assert O.rel_l2(O.generator_forward(st, g["x"], training=False), g["y_eval"]) < 2e-5
 
 
+@pytest.mark.parametrize("n_suffix", [1, 2])
+def test_progressive_generator_matches_reference(golden_dir, n_suffix):
+    """model_generator_progressive.py (the reference's older chained-suffix design)."""
+    g = _load(golden_dir, f"progressive_suffix{n_suffix}")
+    st = S.progressive_state(g["seed"], n_blocks=2, nf=64, n_suffix=n_suffix)
+    names = O.trainable_names(st)
+    leaf = O._leaf(st, names)
+    y = O.progressive_forward(leaf, g["x"], training=True)
+    assert y.shape == g["y"].shape == (2, 3, 8 * 2 ** n_suffix, 8 * 2 ** n_suffix)
+    assert O.rel_l2(y.detach(), g["y"]) < 2e-5
+    grads = dict(zip(names, torch.autograd.grad((y * g["gy"]).sum(), [leaf[k] for k in names])))
+    for k, ref in g["grads"].items():
+        if g["grad_norms"][k] > 1e-3 * max(g["grad_norms"].values()):
+            assert O.rel_l2(grads[k], ref) < 1e-4, k
+    assert O.rel_l2(O.progressive_forward(st, g["x"], training=False), g["y_eval"]) < 2e-5
+
+
 def test_discriminator_matches_reference(golden_dir):
     g = _load(golden_dir, "discriminator")
     st = S.discriminator_state(g["seed"], g["shape"], g["features"], g["strides"])
