@@ -346,20 +346,32 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long long
   for (int i = threadIdx.x; i < classes * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int tpr = C / 8;
-  const int rpb = blockDim.x / tpr;
+  const int rpb = blockDim.x / tpr;          // even (C <= 1024), so a thread's rows keep their x parity
   const int r = threadIdx.x / tpr, cv = threadIdx.x % tpr;
   if (r < rpb) {
-    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < rows;
-         row += static_cast<long long>(gridDim.x) * rpb) {
-      const int cls = ps ? static_cast<int>(((row / W2) & 1) * 2 + (row & 1)) : 0;
+    float acc[2][8];                         // [y parity][channel]; without PixelShuffle only [0]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    const long long first = static_cast<long long>(blockIdx.x) * rpb + r;
+    for (long long row = first; row < rows; row += static_cast<long long>(gridDim.x) * rpb) {
+      const bool odd = ps && ((row / W2) & 1);
       const uint4 u = *reinterpret_cast<const uint4*>(dy + row * C + cv * 8);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __bfloat1622float2(h[j]);
-        atomicAdd(&s_acc[cls * C + cv * 8 + 2 * j], f.x);
-        atomicAdd(&s_acc[cls * C + cv * 8 + 2 * j + 1], f.y);
+        acc[0][2 * j] += odd ? 0.f : f.x;
+        acc[0][2 * j + 1] += odd ? 0.f : f.y;
+        acc[1][2 * j] += odd ? f.x : 0.f;
+        acc[1][2 * j + 1] += odd ? f.y : 0.f;
       }
+    }
+    const int xpar = ps ? static_cast<int>(first & 1) : 0;
+#pragma unroll
+    for (int yp = 0; yp < 2; ++yp) {
+      if (yp && !ps) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[(yp * 2 + xpar) * C + cv * 8 + j], acc[yp][j]);
     }
   }
   __syncthreads();

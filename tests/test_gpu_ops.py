@@ -54,6 +54,9 @@ CONV_CASES = [
     (2, 16, 16, 3, 64, 3, 1, 1, "leaky", 0),      # D / VGG first conv (CUDA cores)
     (2, 9, 7, 64, 64, 3, 1, 1, "none", 0),        # odd, non-square spatial size
     (2, 9, 9, 64, 64, 3, 2, 1, "none", 0),        # stride 2 on odd size (CUDA-core dgrad)
+    (3, 11, 13, 3, 64, 3, 1, 1, "relu", 0),       # thin-in / thin-out streaming kernels, ragged tail
+    (1, 5, 3, 3, 64, 3, 1, 1, "none", 0),         # fewer pixels than one 16-pixel group
+    (2, 40, 24, 3, 64, 3, 1, 1, "leaky", 0),      # several row bands per image
 ]
 
 
@@ -107,10 +110,11 @@ def test_conv_forward_backward(cuda, case):
         assert abs(float(sd.grad) - float(sr.grad)) < 2e-2 * abs(float(sr.grad)) + 3e-3 * scale
 
 
-def test_conv_tanh_nchw_output(cuda):
+@pytest.mark.parametrize("hw", [(12, 12), (9, 7), (37, 20)])
+def test_conv_tanh_nchw_output(cuda, hw):
     from sisr_b200 import ops
     g = torch.Generator().manual_seed(5)
-    x = bf(torch.randn(2, 64, 12, 12, generator=g))
+    x = bf(torch.randn(2, 64, *hw, generator=g))
     wt = torch.randn(3, 64, 3, 3, generator=g) / 24
     b = torch.randn(3, generator=g) * 0.1
     xr, wr, br = x.clone().requires_grad_(True), bf(wt).requires_grad_(True), b.clone().requires_grad_(True)
@@ -120,7 +124,7 @@ def test_conv_tanh_nchw_output(cuda):
     xd, wd, bd = nhwc(x).requires_grad_(True), wt.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
     y, _ = ops.Conv2dFn.apply(xd, wd, bd, None, None, None,
                               ops.ConvCfg(act=ops.ACT_TANH, out_nchw_f32=True))
-    assert y.dtype == torch.float32 and y.shape == (2, 3, 12, 12)
+    assert y.dtype == torch.float32 and y.shape == (2, 3, *hw)
     assert rel(y, y_ref) < 1e-3
     y.backward(gy.cuda())
     assert rel(nchw(xd.grad), xr.grad) < TOL_BF16

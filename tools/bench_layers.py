@@ -27,6 +27,8 @@ LAYERS = [  # name, h, cin, cout, stride, ps_r, stats, count per step (fwd)
     ("V 256->512 @12", 12, 256, 512, 1, 0, False, 2),
     ("V 512->512 @12", 12, 512, 512, 1, 0, False, 6),
     ("V 512->512 @6", 6, 512, 512, 1, 0, False, 8),
+    ("thin 3->64 @96", 96, 3, 64, 1, 0, False, 5),
+    ("thin 64->3 @96", 96, 64, 3, 1, 0, False, 1),
 ]
 REP = 12
 
@@ -45,7 +47,7 @@ def run(kind, name, h, cin, cout, stride, ps, stats):
         else:
             y = torch.randn(B, oh, oh, cout, device=dev).to(torch.bfloat16)
         dx = torch.empty_like(x)
-        st = torch.empty(2 * cout, device=dev) if stats else None
+        st = torch.empty(_lib.query("sisr_stats_rows") * 2 * cout, device=dev) if stats else None
         gp = torch.empty(cout, 3, 3, cin, device=dev)
         db = torch.empty(cout, device=dev)
         ws = torch.empty(max(_lib.query("sisr_conv_wgrad_workspace_bytes", d), 4), dtype=torch.uint8, device=dev)
