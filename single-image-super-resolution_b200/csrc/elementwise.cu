@@ -30,6 +30,18 @@ __device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
   }
   return r;
 }
+__device__ __forceinline__ Vec8 cvt8(const uint4& u) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  Vec8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+constexpr int kRowsPerTrip = 4;   // independent 16-byte load pairs in flight per thread in the BN backward loops
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
   uint4 u;
   u.x = pack_bf16x2(r.v[0], r.v[1]);
@@ -74,6 +86,29 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
     const int h = static_cast<int>(p % H);
     const int n = static_cast<int>(p / H);
     y[i] = __float2bfloat16_rn(x[((static_cast<long long>(n) * C + c) * H + h) * W + w]);
+  }
+}
+// images (C <= 4): one thread per pixel, 64-bit pixel indices avoided (one division per thread)
+template <int C>
+__global__ void nchw_f32_to_nhwc_bf16_small_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                   long long npix, int HW) {
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < npix;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = q / HW;
+    const float* src = x + (n * C) * HW + (q - n * HW);
+#pragma unroll
+    for (int c = 0; c < C; ++c) y[q * C + c] = __float2bfloat16_rn(src[static_cast<size_t>(c) * HW]);
+  }
+}
+template <int C>
+__global__ void nhwc_bf16_to_nchw_f32_small_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+                                                   long long npix, int HW) {
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < npix;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = q / HW;
+    float* dst = y + (n * C) * HW + (q - n * HW);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[static_cast<size_t>(c) * HW] = __bfloat162float(x[q * C + c]);
   }
 }
 // tiled transpose per image: [HW, C] bf16 -> [C, HW] f32 (and back)
@@ -329,28 +364,30 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
       sc[j] = scale[cv * 8 + j];
       sh[j] = shift[cv * 8 + j];
     }
-    // 2 rows per trip: 4 independent 16-byte loads in flight per thread
+    // kRowsPerTrip rows per trip, kept as raw 16-byte words until used
+    constexpr int U = kRowsPerTrip;
     const long long stride = static_cast<long long>(gridDim.x) * rpb;
-    for (long long row0 = static_cast<long long>(blockIdx.x) * rpb + r; row0 < M; row0 += 2 * stride) {
-      Vec8 d[2], v[2];
+    for (long long row0 = static_cast<long long>(blockIdx.x) * rpb + r; row0 < M; row0 += U * stride) {
+      uint4 dr[U], vr[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long row = row0 + u * stride;
         if (row < M) {
-          d[u] = load8(dout + row * C + cv * 8);
-          v[u] = load8(y + row * C + cv * 8);
+          dr[u] = *reinterpret_cast<const uint4*>(dout + row * C + cv * 8);
+          vr[u] = *reinterpret_cast<const uint4*>(y + row * C + cv * 8);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (row0 + u * stride >= M) break;
+        const Vec8 d = cvt8(dr[u]), v = cvt8(vr[u]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(v[u].v[j], sc[j], sh[j]);
-          const float g = d[u].v[j] * act_grad(z, act, sl);
+          const float z = fmaf(v.v[j], sc[j], sh[j]);
+          const float g = d.v[j] * act_grad(z, act, sl);
           p[0][j] += g;
-          p[1][j] += g * (v[u].v[j] - mu[j]) * is[j];
-          if (act == ACT_PRELU) sa += d[u].v[j] * fminf(z, 0.f);
+          p[1][j] += g * (v.v[j] - mu[j]) * is[j];
+          if (act == ACT_PRELU) sa += d.v[j] * fminf(z, 0.f);
         }
       }
     }
@@ -415,26 +452,28 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
       k2[j] = sums[C + c] * inv_count;
     }
     const long long stride = static_cast<long long>(gridDim.x) * rpb;
-    for (long long row0 = static_cast<long long>(blockIdx.x) * rpb + r; row0 < M; row0 += 2 * stride) {
-      Vec8 d[2], v[2];
+    constexpr int U = kRowsPerTrip;
+    for (long long row0 = static_cast<long long>(blockIdx.x) * rpb + r; row0 < M; row0 += U * stride) {
+      uint4 dr[U], vr[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long row = row0 + u * stride;
         if (row < M) {
-          d[u] = load8(dout + row * C + cv * 8);
-          v[u] = load8(y + row * C + cv * 8);
+          dr[u] = *reinterpret_cast<const uint4*>(dout + row * C + cv * 8);
+          vr[u] = *reinterpret_cast<const uint4*>(y + row * C + cv * 8);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long row = row0 + u * stride;
         if (row >= M) break;
+        const Vec8 d = cvt8(dr[u]), v = cvt8(vr[u]);
         Vec8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(v[u].v[j], sc[j], sh[j]);
-          const float g = d[u].v[j] * act_grad(z, act, sl);
-          const float xh = (v[u].v[j] - mu[j]) * is[j];
+          const float z = fmaf(v.v[j], sc[j], sh[j]);
+          const float g = d.v[j] * act_grad(z, act, sl);
+          const float xh = (v.v[j] - mu[j]) * is[j];
           o.v[j] = bf16_round(sc[j] * (g - k1[j] - xh * k2[j]));
           p[0][j] += o.v[j];
         }
@@ -727,7 +766,13 @@ int check() { return cudaGetLastError() == cudaSuccess ? 0 : 4; }
 
 int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int N, int C, int H, int W,
                           cudaStream_t s) {
-  if (C < 32) {
+  if (C == 3 || C == 1) {
+    const long long npix = static_cast<long long>(N) * H * W;
+    if (C == 3)
+      nchw_f32_to_nhwc_bf16_small_kernel<3><<<grid_for(npix, kThreads), kThreads, 0, s>>>(x, y, npix, H * W);
+    else
+      nchw_f32_to_nhwc_bf16_small_kernel<1><<<grid_for(npix, kThreads), kThreads, 0, s>>>(x, y, npix, H * W);
+  } else if (C < 32) {
     const long long total = static_cast<long long>(N) * C * H * W;
     nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, kThreads), kThreads, 0, s>>>(x, y, N, C, H, W);
   } else {
@@ -738,6 +783,11 @@ int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int N, int C, int H,
 }
 int nhwc_bf16_to_nchw_f32(const __nv_bfloat16* x, float* y, int N, int C, int H, int W,
                           cudaStream_t s) {
+  if (C == 3) {
+    const long long npix = static_cast<long long>(N) * H * W;
+    nhwc_bf16_to_nchw_f32_small_kernel<3><<<grid_for(npix, kThreads), kThreads, 0, s>>>(x, y, npix, H * W);
+    return check();
+  }
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
   nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, s>>>(x, y, C, H * W);
   return check();

@@ -25,6 +25,16 @@ void load_entry_points() {
       q == cudaDriverEntryPointSuccess)
     g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
 }
+// The encode entry points are driver API: they need a context current on the CALLING thread.  The
+// runtime binds the primary context lazily on a thread's first runtime call, and a PyTorch autograd
+// worker thread may reach a conv backward without having made one (cached allocations, no kernel yet).
+void bind_context() {
+  thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
 }  // namespace
 
 const char* tmap_last_error() { return g_err; }
@@ -32,6 +42,7 @@ const char* tmap_last_error() { return g_err; }
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_elems, uint32_t box_cols, uint32_t box_rows) {
   std::call_once(g_once, load_entry_points);
+  bind_context();
   if (!g_encode_tiled) {
     snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point unavailable");
     return 1;
@@ -57,6 +68,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_tiled_nhwc_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C,
                               uint32_t channels, uint32_t box_w, uint32_t box_h) {
   std::call_once(g_once, load_entry_points);
+  bind_context();
   if (!g_encode_tiled) {
     snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point unavailable");
     return 1;
@@ -81,6 +93,7 @@ int make_tmap_im2col_nhwc_bf16(CUtensorMap* out, const void* base, int N, int H,
                                int lower_w, int lower_h, int upper_w, int upper_h,
                                uint32_t channels, uint32_t pixels, uint32_t trav_stride) {
   std::call_once(g_once, load_entry_points);
+  bind_context();
   if (!g_encode_im2col) {
     snprintf(g_err, sizeof g_err, "cuTensorMapEncodeIm2col entry point unavailable");
     return 1;

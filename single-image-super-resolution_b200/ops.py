@@ -429,6 +429,7 @@ class Conv2dFn(torch.autograd.Function):
                               saved_v, slope)
         if stats is not None:
             ctx.mark_non_differentiable(stats)
+        ctx.set_materialize_grads(False)      # no zero tensor for the gradient of ``stats`` (one fill kernel per layer)
         return y, stats
 
     @staticmethod
@@ -438,6 +439,8 @@ class Conv2dFn(torch.autograd.Function):
         dev = x.device
         st = _stream()
         cout, cin, k, _ = weight.shape
+        if gy is None:                        # only the statistics were used downstream
+            return (None,) * 8
         gy = gy.contiguous()
         dslope = colsum = None
         if cfg.out_nchw_f32:
