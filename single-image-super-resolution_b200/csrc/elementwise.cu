@@ -271,21 +271,22 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
                                 const float* __restrict__ slope_ptr,
                                 const __nv_bfloat16* __restrict__ residual,
                                 __nv_bfloat16* __restrict__ out, long long nvec, int C) {
+  constexpr int U = 4;       // independent 16-byte loads (pairs with a residual) in flight per thread
   const float sl = resolve_slope(act, slope, slope_ptr);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < nvec;
-       i0 += 2 * stride) {
-    Vec8 vv[2], rr[2];
+       i0 += U * stride) {
+    uint4 vv[U], rr[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
       if (i < nvec) {
-        vv[u] = load8(y + i * 8);
-        if (residual) rr[u] = load8(residual + i * 8);
+        vv[u] = *reinterpret_cast<const uint4*>(y + i * 8);
+        if (residual) rr[u] = *reinterpret_cast<const uint4*>(residual + i * 8);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
       if (i >= nvec) break;
       const int c0 = static_cast<int>((i * 8) % C);
@@ -295,12 +296,13 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
       const float4 sh1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
       const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
       const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-      Vec8 v = vv[u];
+      Vec8 v = cvt8(vv[u]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v.v[j] = act_fwd(fmaf(v.v[j], sc[j], sh[j]), act, sl);
       if (residual) {
+        const Vec8 r = cvt8(rr[u]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v.v[j] += rr[u].v[j];
+        for (int j = 0; j < 8; ++j) v.v[j] += r.v[j];
       }
       store8(out + i * 8, v);
     }
@@ -825,7 +827,7 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, int
              int C, cudaStream_t s) {
   if (C % 8) return 1;
   const long long nvec = M * C / 8;
-  bn_apply_kernel<<<grid_for(nvec, 2 * kThreads, 148 * 8), kThreads, 0, s>>>(y, scale, shift, act, slope, slope_ptr,
+  bn_apply_kernel<<<grid_for(nvec, 4 * kThreads, 148 * 8), kThreads, 0, s>>>(y, scale, shift, act, slope, slope_ptr,
                                                                 residual, out, nvec, C);
   return check();
 }

@@ -184,8 +184,57 @@ class SRGANTrainer:
             self._graph_out = self.step(*self._static)
         return self._graph_out
 
+    def replay_from_feed(self, feed: "HostFeed"):
+        """One captured step on the next batch of ``feed`` (pinned host HR patches): the LR input is
+        made on the device (utils.lr_from_hr, train.py:46), the H2D copy of the following batch runs
+        on the feed's copy stream meanwhile."""
+        from .utils import lr_from_hr
+        hr_dev, slot = feed.take()
+        self._static[0].copy_(hr_dev, non_blocking=True)
+        feed.release(slot)
+        size = tuple(self._static[1].shape[-2:])
+        self._static[1].copy_(lr_from_hr(self._static[0], size), non_blocking=True)
+        self._graph.replay()
+        return self._graph_out
+
     def replay(self, img_hr: torch.Tensor, img_lr: torch.Tensor):
         self._static[0].copy_(img_hr, non_blocking=True)
         self._static[1].copy_(img_lr, non_blocking=True)
         self._graph.replay()
         return self._graph_out
+
+
+class HostFeed:
+    """Double-buffered pinned-host -> device input pipeline for ``SRGANTrainer.replay_from_feed``:
+    ``submit`` starts the asynchronous H2D copy of a batch on a copy stream, ``take`` hands the oldest
+    submitted batch to the current stream.  With one batch submitted ahead, the copy of batch i+1
+    overlaps the compute of step i (the reference's DataLoader + ``.to(device)``, train.py:40-46,
+    is synchronous)."""
+
+    def __init__(self, shape, device, depth: int = 2):
+        self.stage = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(depth)]
+        self.copied = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.submitted = self.taken = 0
+
+    def submit(self, hr_host: torch.Tensor):
+        if self.submitted - self.taken >= len(self.stage):
+            raise RuntimeError("HostFeed: every stage buffer holds a batch that has not been taken")
+        b = self.submitted % len(self.stage)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.free[b])       # the step that last read this buffer
+            self.stage[b].copy_(hr_host, non_blocking=True)
+            self.copied[b].record(self.stream)
+        self.submitted += 1
+
+    def take(self):
+        if self.taken >= self.submitted:
+            raise RuntimeError("HostFeed: nothing submitted")
+        b = self.taken % len(self.stage)
+        torch.cuda.current_stream().wait_event(self.copied[b])
+        self.taken += 1
+        return self.stage[b], b
+
+    def release(self, slot: int):
+        self.free[slot].record(torch.cuda.current_stream())

@@ -449,3 +449,37 @@ def test_progressive_x8_step_at_256_vs_oracle(cuda):
     tr2.step(hr2.cuda(), O.lr_from_hr(hr2, (8, 8)).cuda())
     for k, p in g2.named_parameters():
         assert bool((p.detach() != before[k]).any()) == (not k.startswith("base.")), k
+
+
+def test_host_feed_pipeline_matches_direct_replay(cuda, golden_dir):
+    """HostFeed + replay_from_feed (H2D of batch i+1 overlapping step i, LR made on the device) gives the
+    same three losses, step by step, as replay() on device-resident tensors."""
+    import sisr_b200 as m
+    from sisr_b200.train import HostFeed
+    g = _load(golden_dir, "train_step2")
+    hrs = [S.synthetic_hr(g["seed"] + 40 + i, g["B"], g["HR"]) for i in range(4)]
+    keys = ("err_d", "err_g_adv", "err_g_cont")
+    res = []
+    for mode in ("direct", "feed"):
+        tr, _ = _build_step(m, g["seed"], g["shape"], g["features"], g["strides"], g["mask"], g["lr"])
+        lr0 = m.lr_from_hr(hrs[0].cuda(), (g["LR"], g["LR"]))
+        tr.capture(hrs[0].cuda(), lr0, warmup=1)
+        outs = []
+        if mode == "direct":
+            for h in hrs:
+                hd = h.cuda()
+                o = tr.replay(hd, m.lr_from_hr(hd, (g["LR"], g["LR"])))
+                outs.append([float(o[k]) for k in keys])
+        else:
+            pinned = [h.pin_memory() for h in hrs]
+            feed = HostFeed(tuple(hrs[0].shape), torch.device("cuda"))
+            feed.submit(pinned[0])
+            for i in range(len(hrs)):
+                if i + 1 < len(hrs):
+                    feed.submit(pinned[i + 1])
+                o = tr.replay_from_feed(feed)
+                outs.append([float(o[k]) for k in keys])
+            with pytest.raises(RuntimeError):
+                feed.take()
+        res.append(outs)
+    assert res[0] == res[1]          # same kernels, same inputs, same order: bit-identical losses
