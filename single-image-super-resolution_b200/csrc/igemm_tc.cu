@@ -120,19 +120,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t tmem_
                                               int n0, int cout, int n_img, int gh, int gw, bool valid,
                                               float slope, const float* s_bias, float* s_stats, int opy,
                                               int opx) {
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    uint32_t raw[32];
-    tmem_ld_32x32(tmem_tile + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, raw);
-    tmem_ld_wait();
+  // element offset of this thread's pixel row for column chunk c
+  auto chunk_off = [&](int c) -> size_t {
     const int ncol = n0 + c * 32;
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = __uint_as_float(raw[i]) + s_bias[ncol + i];
-      if (e.act != ACT_NONE) x = x > 0.f ? x : x * slope;
-      v[i] = x;
-    }
     int oy, ox, ch;
     if (e.ps_c > 0) {
       const int sub = ncol / e.ps_c;
@@ -144,13 +134,45 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t tmem_
       oy = gh * e.osy + opy;
       ox = gw * e.osx + opx;
     }
-    const size_t off = (static_cast<size_t>(n_img * e.OH + oy) * e.OW + ox) * e.ldc + ch;
-    if (e.mask && valid) {   // fused activation backward of the tensor this gradient belongs to
-      const uint4* m4 = reinterpret_cast<const uint4*>(e.mask + off);
+    return (static_cast<size_t>(n_img * e.OH + oy) * e.OW + ox) * e.ldc + ch;
+  };
+  // fused activation backward of the tensor this gradient belongs to: its 64 mask bytes per chunk are
+  // requested one chunk ahead, so their latency hides behind the TMEM read and the math of this chunk
+  const bool masked = e.mask && valid;
+  uint4 mnext[4];
+  if (masked) {
+    const uint4* m4 = reinterpret_cast<const uint4*>(e.mask + chunk_off(0));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mnext[q] = __ldg(m4 + q);
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t raw[32];
+    tmem_ld_32x32(tmem_tile + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, raw);
+    uint4 mcur[4];
+    if (masked) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mcur[q] = mnext[q];
+      if (c + 1 < BN / 32) {
+        const uint4* m4 = reinterpret_cast<const uint4*>(e.mask + chunk_off(c + 1));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mnext[q] = __ldg(m4 + q);
+      }
+    }
+    tmem_ld_wait();
+    const int ncol = n0 + c * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float x = __uint_as_float(raw[i]) + s_bias[ncol + i];
+      if (e.act != ACT_NONE) x = x > 0.f ? x : x * slope;
+      v[i] = x;
+    }
+    const size_t off = chunk_off(c);
+    if (masked) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 mq = __ldg(m4 + q);
-        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mq);
+        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mcur[q]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 mf = __bfloat1622float2(mh[j]);
@@ -482,15 +504,37 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
     const int segs = p.cout / 8;                           // 16-byte segments per pixel
     if (e.stats)
       for (int i = threadIdx.x - 64; i < 2 * 128; i += 256) s_sum[i] = 0.f;
+    // output pixel (flattened N*OH*OW index) of GEMM row px of tile class cls
+    auto out_pixel = [&](int px, int cls) -> size_t {
+      if (p.flat) return static_cast<size_t>(px);
+      const int n_img = px / hw;
+      const int rem = px - n_img * hw;
+      const int gh = rem / p.GW;
+      const int gw = rem - gh * p.GW;
+      return static_cast<size_t>(n_img * e.OH + gh * e.osy + p.cls.opy[cls]) * e.OW + gw * e.osx + p.cls.opx[cls];
+    };
+    // fused activation backward (mask = the tensor this gradient belongs to): the four 16-byte mask words
+    // a thread needs for its stores of a 32-pixel chunk are requested one chunk ahead
+    uint4 mq[4];
+    auto prefetch_mask = [&](int px0, int cls) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = tid_a + k * active;
+        const int row = idx / segs, seg = idx - row * segs;
+        const int px = px0 + row;
+        if (px < p.M) mq[k] = __ldg(reinterpret_cast<const uint4*>(e.mask + out_pixel(px, cls) * e.ldc + seg * 8));
+      }
+    };
     float s1 = 0.f, s2 = 0.f;   // BN statistics of this channel over this warp's chunks
     uint32_t it = 0, chunk_no = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, use = it >> 1;
       const int cls = tile / p.p_tiles;
+      const int m0 = (tile - cls * p.p_tiles) * kTP;
+      if (e.mask && warp_active) prefetch_mask(m0 + half * 32, cls);   // lands while the MMAs of this tile run
       mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
       tc_fence_after();
       if (warp_active) {
-        const int m0 = (tile - cls * p.p_tiles) * kTP;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kTP;
         uint32_t raw[32];
         tmem_ld_32x32(trow + half * 32, raw);
@@ -528,21 +572,10 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
             const int row = idx / segs, seg = idx - row * segs;
             const int px = px0 + row;
             if (px < p.M) {
-              size_t opix;
-              if (p.flat) {
-                opix = static_cast<size_t>(px);
-              } else {
-                const int n_img = px / hw;
-                const int rem = px - n_img * hw;
-                const int gh = rem / p.GW;
-                const int gw = rem - gh * p.GW;
-                opix = static_cast<size_t>(n_img * e.OH + gh * e.osy + p.cls.opy[cls]) * e.OW + gw * e.osx +
-                       p.cls.opx[cls];
-              }
+              const size_t opix = out_pixel(px, cls);
               uint4 val = *reinterpret_cast<const uint4*>(stage + row * row_words + seg * 4);
               if (e.mask) {
-                const uint4 mq = __ldg(reinterpret_cast<const uint4*>(e.mask + opix * e.ldc + seg * 8));
-                const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mq);
+                const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mq[k]);
                 __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -556,6 +589,7 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
               *reinterpret_cast<uint4*>(e.out + opix * e.ldc + seg * 8) = val;
             }
           }
+          if (e.mask && c + 2 < kTP / 32) prefetch_mask(m0 + (c + 2) * 32, cls);
         }
       }
       tc_fence_before();

