@@ -6,6 +6,7 @@
 #include "linear.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -193,6 +194,232 @@ int launch_gemm(const TA* a, long long lda, const TB* b, long long ldb, float* c
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
 
+// ------------------------------------------------------------------ weight-streaming GEMMs of the head
+// The three GEMMs above move 75 MB each through a one-tile register prefetch and stop at 1.5-2.6 TB/s.
+// The kernels below keep the same mma.sync contraction but stream the operands through a 3-stage
+// cp.async pipeline as RAW bytes (fp32 stays fp32 in shared memory and is rounded to bf16 when a
+// fragment is built), two blocks per SM, so ~64 KB of weight bytes are in flight per SM.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kWsStages = 3;
+// C[M, N] (+)= A[M, K] * W   with M <= 64 per block row, W fp32 streamed once:
+//   BK = true : W(n, k) = w[n * ldw + k]   (head forward:  h = x . W0^T,  A = x bf16)
+//   BK = false: W(k, n) = w[k * ldw + n]   (head dgrad:    dx = dh . W0,  A = dh fp32)
+// K % 64 == 0, N % 64 == 0.  gridDim = (N/64, ceil(M/64), splits); splits > 1: fp32 atomics into zeroed C.
+template <typename TA, bool BK>
+__global__ void __launch_bounds__(256, 2)
+wstream_gemm_kernel(const TA* __restrict__ a, long long lda, const float* __restrict__ w, long long ldw,
+                    float* __restrict__ c, long long ldc, int M, int K, int k_per_split) {
+  constexpr bool A16 = sizeof(TA) == 2;
+  constexpr int PW = BK ? 72 : 68;                    // fp32 pitch of the W tile (conflict-free fragment reads)
+  constexpr int PA = 72;                              // pitch of the A tile in elements
+  constexpr int kWBytes = 64 * PW * 4;
+  constexpr int kABytes = 64 * PA * static_cast<int>(sizeof(TA));
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int n0 = blockIdx.x * 64, m0 = blockIdx.y * 64;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int nk = (kend - kbeg) / 64;
+  auto w_tile = [&](int st) { return reinterpret_cast<float*>(smem_raw + st * (kWBytes + kABytes)); };
+  auto a_tile = [&](int st) { return reinterpret_cast<TA*>(smem_raw + st * (kWBytes + kABytes) + kWBytes); };
+
+  auto load_stage = [&](int st, int kt) {
+    const int k0 = kbeg + kt * 64;
+    float* ws = w_tile(st);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                     // 64 rows x 16 chunks of 16 B
+      const int idx = tid + i * 256, row = idx >> 4, ch = idx & 15;
+      const float* src = BK ? w + static_cast<long long>(n0 + row) * ldw + k0 + ch * 4
+                            : w + static_cast<long long>(k0 + row) * ldw + n0 + ch * 4;
+      cp_async16(smem_u32(ws + row * PW + ch * 4), src);
+    }
+    TA* as = a_tile(st);
+    constexpr int kChunks = A16 ? 8 : 16;             // 16-byte chunks per 64-element row
+#pragma unroll
+    for (int i = 0; i < kChunks / 4; ++i) {
+      const int idx = tid + i * 256, row = idx / kChunks, ch = idx - row * kChunks;
+      TA* dst = as + row * PA + ch * (16 / static_cast<int>(sizeof(TA)));
+      if (m0 + row < M)
+        cp_async16(smem_u32(dst), a + static_cast<long long>(m0 + row) * lda + k0 + ch * (16 / static_cast<int>(sizeof(TA))));
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  };
+
+  float acc[4][4] = {};
+#pragma unroll
+  for (int s_ = 0; s_ < kWsStages - 1; ++s_) {
+    if (s_ < nk) load_stage(s_, s_);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<kWsStages - 2>();
+    __syncthreads();
+    if (kt + kWsStages - 1 < nk) load_stage((kt + kWsStages - 1) % kWsStages, kt + kWsStages - 1);
+    cp_async_commit();
+    const float* ws = w_tile(kt % kWsStages);
+    const TA* as = a_tile(kt % kWsStages);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      if constexpr (A16) {
+        ldsm_x4(smem_u32(as + (wm * 16 + (lane & 15)) * PA + ks * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
+      } else {
+        const float* ar = reinterpret_cast<const float*>(as) + (wm * 16 + g) * PA + ks * 16 + 2 * t;
+        const float2 f0 = *reinterpret_cast<const float2*>(ar);
+        const float2 f1 = *reinterpret_cast<const float2*>(ar + 8 * PA);
+        const float2 f2 = *reinterpret_cast<const float2*>(ar + 8);
+        const float2 f3 = *reinterpret_cast<const float2*>(ar + 8 * PA + 8);
+        a0 = pack_bf16x2(f0.x, f0.y); a1 = pack_bf16x2(f1.x, f1.y);
+        a2 = pack_bf16x2(f2.x, f2.y); a3 = pack_bf16x2(f3.x, f3.y);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = wn * 32 + nt * 8 + g;
+        uint32_t b0, b1;
+        if constexpr (BK) {
+          const float* br = ws + n * PW + ks * 16 + 2 * t;
+          const float2 f0 = *reinterpret_cast<const float2*>(br);
+          const float2 f1 = *reinterpret_cast<const float2*>(br + 8);
+          b0 = pack_bf16x2(f0.x, f0.y);
+          b1 = pack_bf16x2(f1.x, f1.y);
+        } else {
+          const float* br = ws + (ks * 16 + 2 * t) * PW + n;
+          b0 = pack_bf16x2(br[0], br[PW]);
+          b1 = pack_bf16x2(br[8 * PW], br[9 * PW]);
+        }
+        mma_bf16(acc[nt], a0, a1, a2, a3, b0, b1);
+      }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int gm = m0 + wm * 16 + g + hh * 8;
+      const int gn = n0 + wn * 32 + nt * 8 + 2 * t;
+      if (gm >= M) continue;
+      float* dst = c + gm * ldc + gn;
+      if (gridDim.z > 1) {
+        atomicAdd(dst, acc[nt][hh * 2]);
+        atomicAdd(dst + 1, acc[nt][hh * 2 + 1]);
+      } else {
+        *reinterpret_cast<float2*>(dst) = make_float2(acc[nt][hh * 2], acc[nt][hh * 2 + 1]);
+      }
+    }
+}
+
+template <typename TA, bool BK>
+int launch_wstream(const TA* a, long long lda, const float* w, long long ldw, float* c, long long ldc, int M,
+                   int N, int K, cudaStream_t s) {
+  constexpr int PW = BK ? 72 : 68;
+  constexpr int smem = kWsStages * (64 * PW * 4 + 64 * 72 * static_cast<int>(sizeof(TA)));
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wstream_gemm_kernel<TA, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return 4;
+    configured = true;
+  }
+  const int tiles = (N / 64) * ((M + 63) / 64);
+  int splits = 1;
+  if (tiles < 148) {
+    splits = (148 * 2 + tiles - 1) / tiles;
+    if (splits > K / 256) splits = K / 256;
+    if (splits < 1) splits = 1;
+  }
+  int kps = ((K / 64 + splits - 1) / splits) * 64;
+  splits = (K + kps - 1) / kps;
+  if (splits > 1) cudaMemsetAsync(c, 0, sizeof(float) * static_cast<size_t>(M) * ldc, s);
+  dim3 grid(N / 64, (M + 63) / 64, splits);
+  wstream_gemm_kernel<TA, BK><<<grid, 256, smem, s>>>(a, lda, w, ldw, c, ldc, M, K, kps);
+  return cudaGetLastError() == cudaSuccess ? 0 : 4;
+}
+
+// dW[m, n] = sum_{b < B} dh[b, m] * x[b, n]   (B <= 64: one k-tile; fp32 output written once, 75 MB)
+// One block = 64 rows m (A fragments of dh^T live in registers) x a strided set of 64-column tiles of x,
+// streamed through a 3-stage cp.async pipeline.  gridDim = (column groups, mid / 64).
+__global__ void __launch_bounds__(256, 2)
+dhead_wgrad_kernel(const float* __restrict__ dh, int mid, const __nv_bfloat16* __restrict__ x, long long ldx,
+                   float* __restrict__ dw, long long ldw, int B, int n_tiles) {
+  constexpr int PD = 68;                              // fp32 pitch of the dh tile [k = sample][m]
+  __shared__ __align__(16) float dhs[64 * PD];
+  __shared__ __align__(16) __nv_bfloat16 xs[kWsStages][64 * kLd];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int m0 = blockIdx.y * 64;
+  for (int i = tid; i < 64 * 16; i += 256) {          // dh tile: 64 samples x 64 features
+    const int row = i >> 4, ch = i & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < B) v = *reinterpret_cast<const float4*>(dh + static_cast<long long>(row) * mid + m0 + ch * 4);
+    *reinterpret_cast<float4*>(dhs + row * PD + ch * 4) = v;
+  }
+  auto load_x = [&](int st, int tile) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                     // 64 samples x 8 chunks of 16 B
+      const int idx = tid + i * 256, row = idx >> 3, ch = idx & 7;
+      __nv_bfloat16* dst = xs[st] + row * kLd + ch * 8;
+      if (row < B)
+        cp_async16(smem_u32(dst), x + static_cast<long long>(row) * ldx + static_cast<long long>(tile) * 64 + ch * 8);
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  };
+  const int first = blockIdx.x, step = gridDim.x;
+  const int mine = first < n_tiles ? (n_tiles - first + step - 1) / step : 0;
+#pragma unroll
+  for (int s_ = 0; s_ < kWsStages - 1; ++s_) {
+    if (s_ < mine) load_x(s_, first + s_ * step);
+    cp_async_commit();
+  }
+  __syncthreads();
+  uint32_t af[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const float* ar = dhs + (ks * 16 + 2 * t) * PD + wm * 16 + g;     // A(m, k) = dh[k][m]
+    af[ks][0] = pack_bf16x2(ar[0], ar[PD]);
+    af[ks][1] = pack_bf16x2(ar[8], ar[PD + 8]);
+    af[ks][2] = pack_bf16x2(ar[8 * PD], ar[9 * PD]);
+    af[ks][3] = pack_bf16x2(ar[8 * PD + 8], ar[9 * PD + 8]);
+  }
+  for (int it = 0; it < mine; ++it) {
+    cp_async_wait<kWsStages - 2>();
+    __syncthreads();
+    if (it + kWsStages - 1 < mine) load_x((it + kWsStages - 1) % kWsStages, first + (it + kWsStages - 1) * step);
+    cp_async_commit();
+    const __nv_bfloat16* bt = xs[it % kWsStages];
+    float acc[4][4] = {};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_trans(smem_u32(bt + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kLd + wn * 32 + np * 16 +
+                               ((lane >> 4) << 3)),
+                      b0, b1, b2, b3);
+        mma_bf16(acc[2 * np], af[ks][0], af[ks][1], af[ks][2], af[ks][3], b0, b1);
+        mma_bf16(acc[2 * np + 1], af[ks][0], af[ks][1], af[ks][2], af[ks][3], b2, b3);
+      }
+    const long long nb = static_cast<long long>(first + it * step) * 64;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float* dst = dw + static_cast<long long>(m0 + wm * 16 + g + hh * 8) * ldw + nb + wn * 32 + nt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(dst) = make_float2(acc[nt][hh * 2], acc[nt][hh * 2 + 1]);
+      }
+  }
+  cp_async_wait<0>();
+}
+
 __device__ __forceinline__ float block_sum256(float v, float* scratch) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -240,14 +467,26 @@ __global__ void dhead_tail_bwd_kernel(const float* __restrict__ h, const float* 
   if (threadIdx.x == 0) atomicAdd(db2, dz);
 }
 
+// first-generation GEMMs on request (A/B): SISR_HEAD_V1=1
+bool head_v1() {
+  static const bool v = [] { const char* e = getenv("SISR_HEAD_V1"); return e && e[0] == '1'; }();
+  return v;
+}
+
 }  // namespace
 
 int dhead_forward(const __nv_bfloat16* x_flat, const float* w0, const float* b0, const float* w2,
                   const float* b2, float slope, float* h, float* p, int B, int fc_in, int fc_mid,
                   cudaStream_t s) {
-  if (int rc = launch_gemm<__nv_bfloat16, float, true, true>(x_flat, fc_in, w0, fc_in, h, fc_mid, B, fc_mid,
-                                                             fc_in, s))
+  const bool stream_ok = fc_in % 64 == 0 && fc_mid % 64 == 0 && !head_v1() &&
+                         (reinterpret_cast<uintptr_t>(w0) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_flat) & 15) == 0;
+  if (stream_ok) {
+    if (int rc = launch_wstream<__nv_bfloat16, true>(x_flat, fc_in, w0, fc_in, h, fc_mid, B, fc_mid, fc_in, s))
+      return rc;
+  } else if (int rc = launch_gemm<__nv_bfloat16, float, true, true>(x_flat, fc_in, w0, fc_in, h, fc_mid, B,
+                                                                    fc_mid, fc_in, s)) {
     return rc;
+  }
   dhead_tail_fwd_kernel<<<B, 256, 0, s>>>(h, b0, w2, b2, slope, p, fc_mid);
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
@@ -260,17 +499,28 @@ int dhead_backward(const __nv_bfloat16* x_flat, const float* w0, const float* w2
   cudaMemsetAsync(dw2, 0, sizeof(float) * fc_mid, s);
   cudaMemsetAsync(db2, 0, sizeof(float), s);
   dhead_tail_bwd_kernel<<<B, 256, 0, s>>>(h, w2, p, dp, slope, dh, dw2, db2, db0, fc_mid);
+  const bool stream_ok = fc_in % 64 == 0 && fc_mid % 64 == 0 && !head_v1() &&
+                         (reinterpret_cast<uintptr_t>(w0) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_flat) & 15) == 0;
   if (need_wgrad) {
     // dW0[m=fc_mid, n=fc_in] = sum_b dh[b,m] * x[b,n]
-    if (int rc = launch_gemm<float, __nv_bfloat16, false, false>(dh, fc_mid, x_flat, fc_in, dw0, fc_in, fc_mid,
-                                                               fc_in, B, s))
+    if (stream_ok && B <= 64 && (reinterpret_cast<uintptr_t>(dw0) & 7) == 0) {
+      const int n_tiles = fc_in / 64;
+      dim3 grid(n_tiles < 37 ? n_tiles : 37, fc_mid / 64);
+      dhead_wgrad_kernel<<<grid, 256, 0, s>>>(dh, fc_mid, x_flat, fc_in, dw0, fc_in, B, n_tiles);
+    } else if (int rc = launch_gemm<float, __nv_bfloat16, false, false>(dh, fc_mid, x_flat, fc_in, dw0, fc_in,
+                                                                        fc_mid, fc_in, B, s)) {
       return rc;
+    }
   }
   if (dx_flat) {
     // dx[b, n=fc_in] = sum_k dh[b,k] * W0[k,n]
-    if (int rc = launch_gemm<float, float, true, false>(dh, fc_mid, w0, fc_in, dx_flat, fc_in, B, fc_in,
-                                                       fc_mid, s))
+    if (stream_ok) {
+      if (int rc = launch_wstream<float, false>(dh, fc_mid, w0, fc_in, dx_flat, fc_in, B, fc_in, fc_mid, s))
+        return rc;
+    } else if (int rc = launch_gemm<float, float, true, false>(dh, fc_mid, w0, fc_in, dx_flat, fc_in, B, fc_in,
+                                                                fc_mid, s)) {
       return rc;
+    }
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
