@@ -271,6 +271,7 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
                                 const float* __restrict__ slope_ptr,
                                 const __nv_bfloat16* __restrict__ residual,
                                 __nv_bfloat16* __restrict__ out, long long nvec, int C) {
+  pdl_launch_dependents();
   constexpr int U = 4;       // independent 16-byte loads (pairs with a residual) in flight per thread
   const float sl = resolve_slope(act, slope, slope_ptr);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -434,6 +435,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
                     float slope, const float* __restrict__ slope_ptr, const float* __restrict__ sums,
                     float inv_count, __nv_bfloat16* __restrict__ dy, float* __restrict__ colsum,
                     long long M, int C) {
+  pdl_launch_dependents();
   __shared__ __align__(16) float s_red[kRedFloats];
   const float sl = resolve_slope(act, slope, slope_ptr);
   const int tpr = C / 8;
@@ -496,6 +498,7 @@ __global__ void __launch_bounds__(kThreads)
 act_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, int act,
                float slope, const float* __restrict__ slope_ptr, __nv_bfloat16* __restrict__ din,
                float* __restrict__ dslope, float* __restrict__ colsum, long long M, int C) {
+  pdl_launch_dependents();
   __shared__ __align__(16) float s_red[kRedFloats];
   __shared__ float s_part[kThreads / 32];
   const float sl = resolve_slope(act, slope, slope_ptr);
@@ -541,6 +544,7 @@ act_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
 // ------------------------------------------------------------------ 2x2 max-pool
 __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                     int N, int H, int W, int C) {
+  pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2, cv = C / 8;
   const long long total = static_cast<long long>(N) * OH * OW * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -564,6 +568,7 @@ __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                     const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
                                     int N, int H, int W, int C) {
+  pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2, cv = C / 8;
   const long long total = static_cast<long long>(N) * OH * OW * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;

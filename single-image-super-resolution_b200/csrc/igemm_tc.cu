@@ -22,6 +22,7 @@
 //     the activation traffic drops 9x.  When the whole weight matrix is 9 B tiles (Cin = 64, one N
 //     tile) it is loaded once per CTA and stays resident.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "igemm.h"
 #include "ptx.cuh"
@@ -279,6 +280,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -425,6 +428,8 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -674,6 +679,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -793,6 +800,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
+int g_pdl = [] { const char* e = getenv("SISR_PDL"); return e && e[0] == '1' ? 1 : 0; }();
+
 template <typename K, typename P>
 int launch_kernel(K kernel, bool* configured, int smem_bytes, const CUtensorMap& ta, const CUtensorMap& tb,
                   const P& kp, int grid, cudaStream_t stream, int threads = kThreads) {
@@ -804,7 +813,23 @@ int launch_kernel(K kernel, bool* configured, int smem_bytes, const CUtensorMap&
     }
     *configured = true;
   }
-  kernel<<<grid, threads, smem_bytes, stream>>>(ta, tb, kp);
+  if (g_pdl) {
+    // the prologue (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the
+    // previous kernel in the stream; every kernel of this file calls pdl_wait() before touching memory
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, ta, tb, kp);
+  } else {
+    kernel<<<grid, threads, smem_bytes, stream>>>(ta, tb, kp);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "igemm launch: %s", cudaGetErrorString(e));

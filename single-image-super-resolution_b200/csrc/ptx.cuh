@@ -185,6 +185,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 // ---------------------------------------------------------------- misc
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream still runs; pdl_wait() blocks until that predecessor has
+// completed and its memory is visible (no-op for a normal launch).  pdl_launch_dependents() lets the
+// dependents of THIS grid start early (no-op unless they were launched with the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
