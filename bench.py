@@ -438,6 +438,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     peaks = measured_peaks()
     dom = time_dominant_kernel(dev, batch)
@@ -494,9 +495,10 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": 8 / sec, "unit": "patches/s", "cores": threads, "kind": "port",
                                 "sample": "1 step of batch 8 after 1 warm-up step (oracle port of the "
                                           "reference step, fp32, all host threads)"}
-    print(json.dumps(line), flush=True)
-    if world > 1:
+    if world > 1:                 # tear the process group down first: the JSON line is the last thing printed
         dist.barrier()
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
 
 
 def main():
