@@ -35,24 +35,23 @@ class BasicBlock(nn.Module):
 class Discriminator(nn.Module):
     def __init__(self, input_shape, list_n_features, list_stride):
         super().__init__()
-        w, h = input_shape[1], input_shape[2]
-        for s in list_stride:
-            assert s in (1, 2), "l'article utilise des stride de 1 ou 2 seulement"
-        assert w * h % 4 ** (sum(list_stride) - len(list_stride)) == 0, \
-            "chaque stride à 2 divisise la taille par 2, il faut que ca soit divisible"
-        assert len(list_n_features) == len(list_stride)
-        self.fc_in = w * h * list_n_features[-1] // (4 ** (sum(list_stride) - len(list_stride)))
-        self.fc_mid = list_n_features[-1] * 2
-        self.conv = nn.Sequential(
-            SNConv2d(input_shape[0], list_n_features[0], 3, list_stride[0], 1, sn=True),
-            nn.LeakyReLU(),
-            nn.Sequential(*[BasicBlock(list_n_features[i - 1], list_n_features[i], list_stride[i])
-                            for i in range(1, len(list_n_features))]))
-        self.fc = nn.Sequential(
-            nn.Linear(self.fc_in, self.fc_mid),
-            nn.LeakyReLU(),
-            nn.Linear(self.fc_mid, 1),
-            nn.Sigmoid())
+        channels, width, height = input_shape
+        widths, strides = list(list_n_features), list(list_stride)
+        # the reference's three constructor checks (model_discriminator.py:27-32), same exception type
+        if any(s not in (1, 2) for s in strides):
+            raise AssertionError("strides must be 1 or 2 (SRGAN uses no other)")
+        shrink = 4 ** sum(1 for s in strides if s == 2)        # every stride-2 conv quarters the pixel count
+        if (width * height) % shrink:
+            raise AssertionError("input size is not divisible by the total down-sampling factor")
+        if len(widths) != len(strides):
+            raise AssertionError("list_n_features and list_stride differ in length")
+        self.fc_in = width * height * widths[-1] // shrink     # flattened size entering the head
+        self.fc_mid = 2 * widths[-1]
+        stem = SNConv2d(channels, widths[0], 3, strides[0], 1, sn=True)
+        stages = [BasicBlock(n_in, n_out, st) for n_in, n_out, st in zip(widths[:-1], widths[1:], strides[1:])]
+        self.conv = nn.Sequential(stem, nn.LeakyReLU(), nn.Sequential(*stages))
+        self.fc = nn.Sequential(nn.Linear(self.fc_in, self.fc_mid), nn.LeakyReLU(),
+                                nn.Linear(self.fc_mid, 1), nn.Sigmoid())
 
     def forward(self, x):
         ops.prepare_convs([self.conv[0]] + [b.layers[0] for b in self.conv[2]], x.requires_grad)
@@ -66,15 +65,14 @@ class Discriminator(nn.Module):
                                  self.fc[2].bias)
 
     def load_state_dict(self, state_dict, strict=True):
-        """strict -> default behaviour; otherwise copy every tensor whose name matches and report
-        shape errors (model_discriminator.py:64-76)."""
+        """strict: ``nn.Module`` behaviour.  Otherwise (model_discriminator.py:64-76) every entry whose name
+        exists here is copied in place; unknown names are skipped and a failing copy (shape mismatch) is
+        reported on stdout instead of raised."""
         if strict:
             return nn.Module.load_state_dict(self, state_dict, strict)
-        own_state = self.state_dict()
-        for name, param in state_dict.items():
-            if name not in own_state:
-                continue
+        mine = self.state_dict()
+        for key in (k for k in state_dict if k in mine):
             try:
-                own_state[name].copy_(param)
-            except Exception as e:  # noqa: BLE001 - mirrors the reference's lenient loader
-                print("dis: lecture échouée pour", name, "  -  ", e)
+                mine[key].copy_(state_dict[key])
+            except Exception as err:  # noqa: BLE001 - lenient by contract
+                print(f"dis: could not load {key}: {err}")
