@@ -549,6 +549,7 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
     const int rpb = 256 / (C / 8);
     long long blocks = (rows + rpb - 1) / rpb;
     if (blocks > 148 * 4) blocks = 148 * 4;
+    if (ps && ((blocks * rpb) & 1)) ++blocks;      // a thread's rows must keep their x parity (even row stride)
     bias_grad_kernel<<<static_cast<int>(blocks), 256, (ps ? 4 : 1) * C * sizeof(float), s>>>(
         dy, rows, C, 2 * ow, ps, dbias);
   }
