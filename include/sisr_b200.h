@@ -48,6 +48,9 @@ int sisr_debug_halo_mode(int mode);
 /* debug / A-B timing: 0 = layers with cout <= 128 use the 128-pixel x cout tiles instead of the
  * 128-channel x 256-pixel (transposed) tiles */
 int sisr_debug_transposed(int on);
+/* 1: convs with Cout % 256 == 0 run on the CTA-pair (tcgen05 cta_group::2, M = 256) kernel.  Round-2 draft:
+ * compiled, not yet validated on hardware; default 0. */
+int sisr_debug_pair_mode(int on);
 /* debug / A-B timing: 0 = weight gradients always use the im2col-fed kernel (never the halo boxes) */
 int sisr_debug_wgrad_halo(int on);
 /* 1 if the tcgen05 implicit-GEMM engine takes this fprop/dgrad shape, 0 if the CUDA-core kernel does */

@@ -381,6 +381,173 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair kernel (Cout % 256 == 0)
+// ROUND-2 DRAFT: compiles for sm_100a, NOT yet run on hardware; reachable only through
+// igemm_set_pair(1) / SISR_PAIR=1 (default off) and the harness.
+// Same im2col-fed pipeline as igemm_tc_kernel<256, .>, but one tile = 256 pixels x 256 channels computed by
+// a CTA pair with tcgen05.mma.cta_group::2 (M = 256): CTA r of the pair loads the im2col rows of pixels
+// [m0 + 128 r, +128) and rows [n0 + 128 r, +128) of the weight tile, i.e. 32 KB per k-block instead of
+// 48 KB, and the per-SM shared-memory operand read per K = 16 step drops from 128 + 256 rows to 128 + 128
+// (the SS-form instruction time follows those rows, profiles/r1_notes.md).
+//   full_bar   : leader only, count 1 (leader's arrive.expect_tx of BOTH CTAs' bytes; both CTAs' TMA
+//                complete_tx on it through the peer-bit-cleared address)
+//   empty_bar, tmem_full_bar : one per CTA, signalled by the leader's multicast tcgen05.commit
+//   tmem_empty_bar : leader only, count 8 (4 epilogue warps of each CTA)
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = kATileBytes + 128 * kBK * 2;      // 32 KB per CTA
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const KParams p) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[kPairStages];
+  __shared__ __align__(8) uint64_t empty_bar[kPairStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_stats[2 * kMaxCout];
+  __shared__ float s_bias[kMaxCout];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int per_class = p.m_tiles * p.n_tiles;            // m_tiles counts 256-pixel tiles here
+  const int num_tiles = per_class * p.cls.n;
+  const int cout = p.n_tiles * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 8);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(smem_u32(&tmem_base_slot), 2 * BN);
+    tmem_relinquish_pair();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < cout; i += 128) s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
+    if (p.e.stats)
+      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) s_stats[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // the peer's barriers are initialised before anything targets them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      const int hw = p.GH * p.GW;
+      uint32_t kbg = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int cls = tile / per_class, t_in = tile - cls * per_class;
+        const int m0 = (t_in / p.n_tiles) * 256 + static_cast<int>(rank) * kBM;
+        const int n0 = (t_in % p.n_tiles) * BN + static_cast<int>(rank) * 128;
+        const int n_img = m0 / hw;
+        const int rem = m0 - n_img * hw;
+        const int gh = rem / p.GW;
+        const int gw = rem - gh * p.GW;
+        const int cw = gw * p.trav_stride + p.lower_w;
+        const int ch = gh * p.trav_stride + p.lower_h;
+        for (int tap = p.cls.tap_begin[cls]; tap < p.cls.tap_begin[cls] + p.cls.tap_count[cls]; ++tap) {
+          for (int cb = 0; cb < p.cin_blocks; ++cb, ++kbg) {
+            const uint32_t s = kbg % kPairStages;
+            const uint32_t round = kbg / kPairStages;
+            mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            if (rank == 0) mbar_expect_tx(fb, 2 * kPairStageBytes);
+            const uint32_t a_dst = smem_u32(smem + s * kPairStageBytes);
+            const uint32_t b_dst = a_dst + kATileBytes;
+            tma_load_im2col_4d_pair(a_dst, &tmap_a, fb, cb * kBK, cw, ch, n_img, p.taps.off_w[tap],
+                                    p.taps.off_h[tap]);
+            tma_load_2d_pair(b_dst, &tmap_b, fb, p.taps.k_off[tap] + cb * kBK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      uint32_t kbg = 0, it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const uint32_t acc = it & 1, use = it >> 1;
+        const int num_kb = p.cls.tap_count[tile / per_class] * p.cin_blocks;
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const uint32_t s = kbg % kPairStages;
+          const uint32_t round = kbg / kPairStages;
+          mbar_wait(smem_u32(&full_bar[s]), round & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem + s * kPairStageBytes);
+            const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16_pair(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(smem_u32(&empty_bar[s]));
+            if (kb == num_kb - 1) umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (both CTAs, own 128 lanes)
+    const int quad = warp & 3;
+    const int hw = p.GH * p.GW;
+    const float slope = resolve_slope(p.e);
+    uint32_t it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const uint32_t acc = it & 1, use = it >> 1;
+      const int cls = tile / per_class, t_in = tile - cls * per_class;
+      const int n0 = (t_in % p.n_tiles) * BN;
+      const int row = (t_in / p.n_tiles) * 256 + static_cast<int>(rank) * kBM + quad * 32 + lane;
+      const bool valid = row < p.M;
+      const int rr = valid ? row : 0;
+      const int n_img = rr / hw;
+      const int rem = rr - n_img * hw;
+      const int gh = rem / p.GW;
+      const int gw = rem - gh * p.GW;
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
+      tc_fence_after();
+      epilogue_tile<BN>(p.e, tmem_base + acc * BN, quad, lane, n0, cout, n_img, gh, gw, valid, slope,
+                        s_bias, s_stats, p.cls.opy[cls], p.cls.opx[cls]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(smem_u32(&tmem_empty_bar[acc]));
+    }
+    if (p.e.stats) flush_stats(p.e, s_stats, cout);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // no MMA of the leader still reads this CTA's shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 2 * BN);
+  }
+}
+
 // ------------------------------------------------------------------ transposed kernel (Cout <= 128)
 constexpr int kTP = 256;                          // pixels per tile (UMMA N)
 constexpr int kTWBytes = 128 * kBK * 2;           // weight tile: 128 rows x 64 k
@@ -800,6 +967,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
+int g_pair = [] { const char* e = getenv("SISR_PAIR"); return e && e[0] == '1' ? 1 : 0; }();
 int g_pdl = [] { const char* e = getenv("SISR_PDL"); return e && e[0] == '1' ? 1 : 0; }();
 
 template <typename K, typename P>
@@ -964,6 +1132,7 @@ const char* igemm_last_error() { return g_err; }
 int igemm_max_ctas() { return num_sms(); }
 void igemm_set_halo_mode(int mode) { g_halo_mode = mode; }
 void igemm_set_transposed(int on) { g_transposed = on; }
+void igemm_set_pair(int on) { g_pair = on; }
 
 bool igemm_supported(const IgemmProblem& p) {
   if (p.Cin % 64 || p.Cout % 64 || p.Cout > kMaxCout) return false;
@@ -1080,6 +1249,21 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   fill_epi(kp.e, p);
   const int tiles = kp.m_tiles * kp.n_tiles * kp.cls.n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (g_pair && bn == 256 && num_sms() >= 2) {
+    // CTA-pair kernel (round-2 draft, off by default): 256-pixel tiles, the weight tile split across the pair
+    CUtensorMap tb2;
+    if (make_tmap_2d_bf16(&tb2, p.w, p.Cout, p.Ktot, p.Ktot, kBK, 128)) {
+      snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
+      return 2;
+    }
+    kp.m_tiles = static_cast<int>((M + 255) / 256);
+    const int ptiles = kp.m_tiles * kp.n_tiles * kp.cls.n;
+    int pairs = num_sms() / 2;
+    if (ptiles < pairs) pairs = ptiles;
+    static bool configured = false;
+    return launch_kernel(igemm_pair_kernel, &configured, kPairStages * kPairStageBytes + 1024, ta, tb2, kp,
+                         2 * pairs, stream, kThreads);
+  }
   switch (bn) {
     case 64:
       return launch_im2col<64, 8>(ta, tb, kp, grid, stream);
