@@ -2,6 +2,7 @@
 
     python single-image-super-resolution_b200/build.py            # libsisr_b200.so
     python single-image-super-resolution_b200/build.py harness    # + build/harness_igemm
+    python single-image-super-resolution_b200/build.py probes     # + build/probe_{shift,pdl,mma}
 
 The shared library lands next to this file so that it travels to the GPU box with the repo
 snapshot (built artefacts are git-ignored).
@@ -62,7 +63,21 @@ def build_harness():
     return out
 
 
+def build_probes():
+    """Stand-alone hardware probes (not part of the library): build/probe_{shift,pdl,mma}."""
+    outs = []
+    for name, extra in (("probe_shift", ["tmap.cpp"]), ("probe_pdl", []), ("probe_mma", [])):
+        out = os.path.join(ROOT, "build", name)
+        srcs = [os.path.join(CSRC, name + ".cu")] + [os.path.join(CSRC, f) for f in extra]
+        if _newer(out, srcs):
+            _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-o", out, *srcs, "-lcudart", "-lcuda"])
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     build_lib(force="--force" in sys.argv, verbose_ptxas="-v" in sys.argv)
     if "harness" in sys.argv:
         build_harness()
+    if "probes" in sys.argv:
+        build_probes()
