@@ -95,3 +95,14 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("# oracle", ""), f
+
+
+def test_bench_reads_dominant_kernel_share_from_committed_profile():
+    """bench.py's roofline.share_of_step is parsed from profiles/r1_step_launches_b64_final_summary.txt."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench_mod", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    text = mod.dominant_share()
+    assert text.startswith("igemm_t_kernel = ") and "%" in text and "launches" in text
