@@ -139,6 +139,32 @@ class emulate_bf16_storage:
         _EMULATE[0] = self.prev
 
 
+class record_taps:
+    """Context manager: the generator functions record named intermediate activations (block
+    outputs, trunk end, stage outputs) into the dict it yields, with ``retain_grad`` so that a later
+    ``backward`` leaves the activation gradient on them - the oracle side of the per-layer parity
+    checks (the CUDA modules expose the same names through ``ops.record_taps``)."""
+
+    def __enter__(self):
+        self.prev = _TAPS[0]
+        _TAPS[0] = {}
+        return _TAPS[0]
+
+    def __exit__(self, *exc):
+        _TAPS[0] = self.prev
+
+
+_TAPS = [None]
+
+
+def _tap(name: str, x: torch.Tensor) -> torch.Tensor:
+    if _TAPS[0] is not None:
+        if x.requires_grad:
+            x.retain_grad()
+        _TAPS[0][name] = x
+    return x
+
+
 def _q(x):      # activation stored as bf16
     return _RoundBF16.apply(x) if _EMULATE[0] else x
 
@@ -228,9 +254,9 @@ def generator_forward_no_end(st: State, x: torch.Tensor, p: str = "", training: 
         x = generator_forward_no_end(st, x, p + "base.", training, scales)
         x = _qg(conv(st, p + "upscale.0.", x, 1, 1, training))
         x = pixel_shuffle(x, 2)
-        return _q(prelu(st, p + "upscale.2.", x))
+        return _tap(p + "upscale", _q(prelu(st, p + "upscale.2.", x)))
     x = _qg(conv(st, p + "first_layers.0.", _q(x), 1, 4, training))
-    x = _q(prelu(st, p + "first_layers.1.", x))
+    x = _tap(p + "first_layers", _q(prelu(st, p + "first_layers.1.", x)))
     skip = x
     n_blocks = _count(st, p + "block_list.{}.layers.0.bias")
     for i in range(n_blocks):
@@ -240,16 +266,16 @@ def generator_forward_no_end(st: State, x: torch.Tensor, p: str = "", training: 
         y = _q(prelu(st, q + "2.", y))
         y = _q(conv(st, q + "3.", y, 1, 1, training))
         y = batch_norm(st, q + "4.", y, training)
-        x = _q(x + y)
+        x = _tap(f"{p}block_list.{i}", _q(x + y))
     x = _q(conv(st, p + "block_list_end.0.", x, 1, 1, training))
     x = batch_norm(st, p + "block_list_end.1.", x, training)
-    x = _q(x + skip)
+    x = _tap(p + "block_list_end", _q(x + skip))
     n_up = _count(st, p + "upscale.{}.0.bias")
     for s in range(n_up):
         q = f"{p}upscale.{s}."
         x = _qg(conv(st, q + "0.", x, 1, 1, training))
         x = pixel_shuffle(x, scales[s] if scales else 2)
-        x = _q(prelu(st, q + "2.", x))
+        x = _tap(f"{p}upscale.{s}", _q(prelu(st, q + "2.", x)))
     return x
 
 

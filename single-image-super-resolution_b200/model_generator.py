@@ -123,18 +123,18 @@ class Generator(nn.Module):
         convs += [stage[0] for stage in self.upscale]
         return convs
 
-    def forward_no_end_nhwc(self, x):
+    def forward_no_end_nhwc(self, x, tap_prefix=""):
         """x: NHWC bf16 LR image -> NHWC bf16 feature map after the upscale stages."""
         conv0, act0 = self.first_layers
         x, _ = conv0.run(x, act=ACT_PRELU, slope=act0.weight)
-        skip = x
-        for block in self.block_list:
-            x = block.forward_nhwc(x)
+        skip = ops.tap(tap_prefix + "first_layers", x)
+        for i, block in enumerate(self.block_list):
+            x = ops.tap(f"{tap_prefix}block_list.{i}", block.forward_nhwc(x))
         conv_e, bn_e = self.block_list_end
         y, st = conv_e.run(x, want_stats=bn_e.training)
-        x = bn_act(bn_e, y, st, residual=skip)
-        for stage in self.upscale:
-            x = stage.forward_nhwc(x)
+        x = ops.tap(tap_prefix + "block_list_end", bn_act(bn_e, y, st, residual=skip))
+        for s, stage in enumerate(self.upscale):
+            x = ops.tap(f"{tap_prefix}upscale.{s}", stage.forward_nhwc(x))
         return x
 
     def forward_no_end(self, x):
@@ -182,8 +182,9 @@ class GeneratorSuffix(nn.Module):
     def convs_no_end(self):
         return self.base.convs_no_end() + [self.upscale[0]]
 
-    def forward_no_end_nhwc(self, x):
-        return self.upscale.forward_nhwc(self.base.forward_no_end_nhwc(x))
+    def forward_no_end_nhwc(self, x, tap_prefix=""):
+        x = self.base.forward_no_end_nhwc(x, tap_prefix + "base.")
+        return ops.tap(tap_prefix + "upscale", self.upscale.forward_nhwc(x))
 
     def forward_no_end(self, x):
         ops.prepare_convs(self.convs_no_end(), x.requires_grad)

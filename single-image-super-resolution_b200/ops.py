@@ -54,6 +54,29 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Named intermediate activations for per-layer parity checks (tests): inside ``record_taps`` the
+# generator records its NHWC bf16 block outputs (``retain_grad`` so that backward leaves the
+# activation gradient on them).  Outside the context ``tap`` is a no-op.
+_taps = [None]
+
+
+@contextlib.contextmanager
+def record_taps():
+    prev, _taps[0] = _taps[0], {}
+    try:
+        yield _taps[0]
+    finally:
+        _taps[0] = prev
+
+
+def tap(name: str, x: torch.Tensor) -> torch.Tensor:
+    if _taps[0] is not None:
+        if x.requires_grad:
+            x.retain_grad()
+        _taps[0][name] = x
+    return x
+
+
 _stats_rows = [0]
 
 

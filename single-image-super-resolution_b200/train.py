@@ -144,9 +144,12 @@ class SRGANTrainer:
 
     # -- checkpoint (same dictionary as utils._save, utils.py:107-114) -----------------------------
     def checkpoint(self, epoch: int = 0) -> dict:
+        """The replay list is exported the way the reference keeps it (fp32 CPU tensors,
+        config.py:53, train.py:60-61), so that ``gen_dis_list`` + ``adversarial_loss_d`` of the reference
+        can resume from this dictionary; in memory it stays bf16 on the GPU."""
         return {"epoch": epoch, "net_g": self.net_g.state_dict(), "net_d": self.net_d.state_dict(),
                 "opti_g": self.opt_g.state_dict(), "opti_d": self.opt_d.state_dict(),
-                "dis_list": list(self.dis_list_old)}
+                "dis_list": [t.float().cpu() for t in self.dis_list_old]}
 
     def restore(self, checkpoint: dict) -> int:
         """Resume as config.py does (config.py:90-92, 296-302, 308-331): non-strict weight loading
@@ -165,7 +168,7 @@ class SRGANTrainer:
                 except Exception as e:  # noqa: BLE001 - mirrors the reference's best-effort load
                     print("erreur chargement optimizers:", e)
         dev = next(self.net_g.parameters()).device
-        self.dis_list_old = [t.to(dev) for t in checkpoint.get("dis_list", [])]
+        self.dis_list_old = [t.to(dev).to(torch.bfloat16) for t in checkpoint.get("dis_list", [])]
         self._graph = None          # a captured graph holds the old optimizer buffers
         return int(checkpoint.get("epoch", 0))
 

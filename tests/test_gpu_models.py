@@ -383,8 +383,27 @@ def test_checkpoint_resume_and_torch_adam_interchange(cuda):
     ref.load_state_dict(ckpt["opti_d"])
     st = ref.state[params[0]]
     assert int(st["step"]) == 2 and st["exp_avg"].shape == params[0].shape
+    sched = torch.optim.lr_scheduler.LambdaLR(ref, lr_lambda=lambda it: 0.9 ** it)   # config.py:170-180
+    for p in params:
+        p.grad = torch.ones_like(p)
+    ref.step()                                     # the reference's optimizer must STEP on our state
+    sched.step()
+    assert int(ref.state[params[0]]["step"]) == 3
     tr2.opt_d.load_state_dict(ref.state_dict())
-    assert int(tr2.opt_d._dev_state[0][0].item()) == 2
+    assert int(tr2.opt_d._dev_state[0][0].item()) == 3
+    assert abs(tr2.opt_d.param_groups[0]["lr"] - lr) < 1e-12      # schedule restarts from initial_lr
+    out = tr2.step(hrs[2].cuda(), lrs[2].cuda())                     # ... and ours on the reference's state
+    assert all(torch.isfinite(out[k]).all() for k in ("err_d", "err_g_adv", "err_g_cont"))
+    assert int(tr2.opt_d._dev_state[0][0].item()) == 4
+    # the replay list is exported as the reference keeps it (fp32, CPU) and comes back as bf16 GPU tensors
+    tr2.cfg.use_replay = True
+    tr2.train_iteration(hrs[0].cuda(), lrs[0].cuda())
+    ck2 = tr2.checkpoint()
+    assert ck2["dis_list"][0].dtype == torch.float32 and not ck2["dis_list"][0].is_cuda
+    st_d = S.discriminator_state(seed + 1, shape, feats, strides)
+    assert O.discriminator_forward(st_d, ck2["dis_list"][0], strides, True).shape == (4, 1)   # fp32 net accepts it
+    tr2.restore(ck2)
+    assert tr2.dis_list_old[0].dtype == torch.bfloat16 and tr2.dis_list_old[0].is_cuda
 
 
 def test_experience_replay_step_vs_oracle(cuda):
