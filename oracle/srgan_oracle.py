@@ -424,47 +424,63 @@ def train_step(g: State, d: State, vgg: State, hr: torch.Tensor, lr_img: torch.T
                w_adv_g: float = 5e-2, w_adv_d: float = 1.0, w_cont: float = 1.0,
                real_label: float = 1.0, real_label_reduced: float = 0.9, fake_label: float = 0.0,
                g_trainable: Optional[Sequence[str]] = None, old_fakes: Sequence[torch.Tensor] = (),
-               lr_scale: float = 1.0) -> Dict[str, object]:
-    """One iteration of train.py:33-122 (supervised mode, replay list passed explicitly).
+               lr_scale: float = 1.0, content_loss_on_lr: bool = False, hr2: Optional[torch.Tensor] = None,
+               cont_kind: str = "features") -> Dict[str, object]:
+    """One iteration of train.py:33-122 (replay list passed explicitly).
 
     ``g``/``d`` are updated in place (weights, SN u/v, BN running stats) exactly as the reference
     modules would be.  Returns losses, the fake batch and the gradients that the optimisers saw.
+    A zero weight skips its branch (train.py:56,86,94,106).  ``content_loss_on_lr`` (train.py:41-50,
+    95-97): the discriminator's real batch is ``hr2`` and the content loss compares ``lr_img`` with the
+    re-downsampled fake; ``cont_kind`` "identity" = model_content_extractor.identity (pixel MSE).
     """
     g_names = list(g_trainable) if g_trainable is not None else trainable_names(g)
     d_names = trainable_names(d)
     gl = _leaf(g, g_names)
     fake = generator_forward(gl, lr_img, training=True)              # train.py:53
+    real_d = hr2 if (content_loss_on_lr and hr2 is not None) else hr
 
     # ---- D update, train.py:56-75 and 128-168
-    dl = _leaf(d, d_names)
-    d_real = discriminator_forward(dl, hr, d_strides, True).view(-1)
-    err_d = bce(d_real, real_label_reduced)
-    d_fake_mean = 0.0
-    for fk in [fake.detach(), *old_fakes]:
-        d_fake = discriminator_forward(dl, fk, d_strides, True).view(-1)
-        err_d = err_d + bce(d_fake, fake_label)
-        d_fake_mean += float(d_fake.mean())
-    err_d = err_d * w_adv_d
-    d_grads = dict(zip(d_names, torch.autograd.grad(err_d, [dl[k] for k in d_names])))
-    for k in ("weight_u", "weight_v", "running_mean", "running_var", "num_batches_tracked"):
-        pass  # buffers were updated in place through the shared tensors of ``d``
-    opt_d.step(d, d_grads, lr_scale)
+    err_d = torch.zeros(())
+    d_fake_mean, d_x, d_grads = 0.0, 0.0, {}
+    if w_adv_d:
+        dl = _leaf(d, d_names)
+        d_real = discriminator_forward(dl, real_d, d_strides, True).view(-1)
+        d_x = float(d_real.detach().mean())
+        err_d = bce(d_real, real_label_reduced)
+        for fk in [fake.detach(), *old_fakes]:
+            d_fake = discriminator_forward(dl, fk, d_strides, True).view(-1)
+            err_d = err_d + bce(d_fake, fake_label)
+            d_fake_mean += float(d_fake.detach().mean())
+        err_d = err_d * w_adv_d
+        d_grads = dict(zip(d_names, torch.autograd.grad(err_d, [dl[k] for k in d_names])))
+        # (buffers were updated in place through the shared tensors of ``d``)
+        opt_d.step(d, d_grads, lr_scale)
 
     # ---- G update, train.py:81-108, 171-186
-    dl2 = _leaf(d, d_names)
-    out = discriminator_forward(dl2, fake, d_strides, True).view(-1)
-    err_g_adv = bce(out, real_label) * w_adv_g
-    feat_real = masked_vgg_forward(vgg, hr, vgg_mask)
-    feat_fake = masked_vgg_forward(vgg, fake, vgg_mask)
-    err_g_cont = torch.mean((feat_real - feat_fake) ** 2) * w_cont
-    err_g = err_g_adv + err_g_cont
-    g_grads = dict(zip(g_names, torch.autograd.grad(err_g, [gl[k] for k in g_names],
-                                                    allow_unused=True)))
-    opt_g.step(g, g_grads, lr_scale)
+    err_g_adv, err_g_cont, d_g_z2, g_grads = torch.zeros(()), torch.zeros(()), 0.0, {}
+    if w_adv_g:
+        dl2 = _leaf(d, d_names)
+        out = discriminator_forward(dl2, fake, d_strides, True).view(-1)
+        d_g_z2 = float(out.detach().mean())
+        err_g_adv = bce(out, real_label) * w_adv_g
+    if w_cont:
+        if content_loss_on_lr:
+            a, b = lr_img, lr_from_hr(fake, tuple(lr_img.shape[-2:]))
+        else:
+            a, b = hr, fake
+        if cont_kind != "identity":
+            a, b = masked_vgg_forward(vgg, a, vgg_mask), masked_vgg_forward(vgg, b, vgg_mask)
+        err_g_cont = torch.mean((a - b) ** 2) * w_cont
+    if w_adv_g or w_cont:
+        err_g = err_g_adv + err_g_cont
+        g_grads = dict(zip(g_names, torch.autograd.grad(err_g, [gl[k] for k in g_names],
+                                                        allow_unused=True)))
+        opt_g.step(g, g_grads, lr_scale)
     return {
         "fake": fake.detach(), "err_d": float(err_d), "err_g_adv": float(err_g_adv),
-        "err_g_cont": float(err_g_cont), "d_x": float(d_real.mean()), "d_g_z1": d_fake_mean,
-        "d_g_z2": float(out.mean()), "d_grads": d_grads, "g_grads": g_grads,
+        "err_g_cont": float(err_g_cont), "d_x": d_x, "d_g_z1": d_fake_mean,
+        "d_g_z2": d_g_z2, "d_grads": d_grads, "g_grads": g_grads,
     }
 
 

@@ -249,6 +249,65 @@ def case_train_step(mg, md, mc, seed, gold, n_steps=2):
     }
 
 
+def case_train_step_branches(mg, md, mc, seed, gold):
+    """Unmodified train.train_loop in the "unsupervised" mode (content_loss_on_lr=True, config.py:24:
+    HR swap train.py:41-50, identity content loss x100 on the re-downsampled fake train.py:95-97, adversarial
+    weight 5e-3) and with epoch-scheduled weights that switch branches off (train.py:56,86,94,106)."""
+    from . import ref_harness as R
+    import model_content_extractor as mce
+    B, HR, LRs = 4, 16, 4
+    shape, feats, strides, mask, lr = (3, HR, HR), [64, 64, 128, 128], [1, 2, 1, 2], 0b00010, 1e-3
+    cases = {
+        # name: (content_loss_on_lr, weights (adv_g, adv_d, cont, kind))
+        "on_lr": (True, (5e-3, 1.0, 100.0, "identity")),
+        "no_adv": (False, (0, 0, 1.0, "features")),          # pre-training on the content loss only
+        "adv_only": (False, (5e-2, 1.0, 0, None)),
+        "identity_x10": (False, (5e-2, 1.0, 10.0, "identity")),
+    }
+    out = {}
+    for name, (on_lr, (wg, wd, wc, kind)) in cases.items():
+        print("train_step branch", name)
+        g_st = S.generator_state(seed, n_blocks=2, n_suffix=1)
+        d_st = S.discriminator_state(seed + 1, shape, feats, strides)
+        v_st = S.vgg_state(seed + 2, mask)
+        hrs = [S.synthetic_hr(seed + 10 + i, B, HR) for i in range(3)]
+        hr2s = [S.synthetic_hr(seed + 30 + i, B, HR) for i in range(3)]
+        net_g = mg.GeneratorSuffix(mg.Generator(2, 64, 256, [2], use_sn=True))
+        net_d = md.Discriminator(shape, feats, strides)
+        ext = mc.MaskedVGG(mask)
+        for net, st in ((net_g, g_st), (net_d, d_st), (ext, v_st)):
+            torch.nn.Module.load_state_dict(net, S.clone_state(st), strict=True)
+        ident = mce.identity()
+        lw = (lambda e, w=wg: w, lambda e, w=wd: w,
+              lambda e, w=wc, k=kind: (w, {"features": ext, "identity": ident, None: None}[k]))
+        batches = [((h, None), (h2, None)) for h, h2 in zip(hrs, hr2s)] if on_lr else hrs
+        d_l, g_l, c_l, _, _ = R.run_train_loop(net_g, net_d, ext, batches, lr=lr, lr_size=LRs,
+                                               content_loss_on_lr=on_lr, loss_weights=lw, identity=ident)
+        og = O.AdamState(O.trainable_names(g_st), lr)
+        od = O.AdamState(O.trainable_names(d_st), lr)
+        for i in range(2):
+            lr_img = O.lr_from_hr(hrs[i], (LRs, LRs))
+            r = O.train_step(g_st, d_st, v_st, hrs[i], lr_img, d_strides=strides, vgg_mask=mask, opt_g=og,
+                             opt_d=od, w_adv_g=wg, w_adv_d=wd, w_cont=wc, content_loss_on_lr=on_lr,
+                             hr2=hr2s[i] if on_lr else None, cont_kind=kind or "features")
+            tol = TOL if i == 0 else 5e-4
+            for key, want in (("err_d", d_l[i]), ("err_g_adv", g_l[i]), ("err_g_cont", c_l[i])):
+                if want == 0.0:
+                    assert r[key] == 0.0, (name, key)
+                else:
+                    _check(f"{name} step{i} {key}", torch.tensor(r[key]), torch.tensor(want), max(tol, 1e-4))
+        # a skipped D update leaves the discriminator untouched (weights AND spectral-norm / BN buffers)
+        if not wd and not wg:
+            ref_d = net_d.state_dict()
+            init = S.discriminator_state(seed + 1, shape, feats, strides)
+            assert all(torch.equal(ref_d[k], init[k]) for k in init), "reference moved D with zero weights"
+            assert all(torch.equal(d_st[k], init[k]) for k in init), "oracle moved D with zero weights"
+        out[name] = {"content_loss_on_lr": on_lr, "weights": (wg, wd, wc, kind),
+                     "err_d": d_l, "err_g_adv": g_l, "err_g_cont": c_l}
+    gold["train_step_branches"] = {"seed": seed, "B": B, "HR": HR, "LR": LRs, "shape": shape, "features": feats,
+                                   "strides": strides, "mask": mask, "lr": lr, "cases": out}
+
+
 def case_lr_from_hr(seed, gold):
     print("lr_from_hr")
     import utils as ref_utils
@@ -319,6 +378,7 @@ def main():
     case_progressive(2, 610, gold)
     case_train_step(mg, md, mc, 500, gold, n_steps=1)
     case_train_step(mg, md, mc, 500, gold, n_steps=2)
+    case_train_step_branches(mg, md, mc, 520, gold)
     os.makedirs(GOLD, exist_ok=True)
     for name, blob in gold.items():
         torch.save(blob, os.path.join(GOLD, name + ".pt"))

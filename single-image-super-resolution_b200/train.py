@@ -20,15 +20,53 @@ from . import ops
 from .optim import Adam
 
 
+def gen_losses(content_loss_on_lr: bool = False, n_g=(0, float("inf")), n_d=(0, float("inf")),
+               n_content=None, n_identity=None):
+    """The epoch-scheduled loss weights of config.gen_losses (config.py:124-166), same defaults: each
+    weight is active for epochs in [start, stop) and 0 outside (a zero weight SKIPS its branch of the step,
+    train.py:56,86,94,106).  ``loss_weight_cont(epoch)`` returns (weight, kind) with kind "features"
+    (the MaskedVGG extractor), "identity" (plain pixel MSE, weight x10) or None; in ``content_loss_on_lr``
+    mode the defaults are adversarial 5e-3 and identity x10 x10 on the re-downsampled fake."""
+    inf = float("inf")
+    if n_content is None:
+        n_content = (0, 0) if content_loss_on_lr else (0, inf)
+    if n_identity is None:
+        n_identity = (0, inf) if content_loss_on_lr else (0, 0)
+
+    def loss_weight_adv_g(i):
+        if n_g[0] <= i < n_g[1]:
+            return 5e-3 if content_loss_on_lr else 5e-2
+        return 0
+
+    def loss_weight_adv_d(i):
+        return 1.0 if n_d[0] <= i < n_d[1] else 0
+
+    def loss_weight_cont(i):
+        cont = n_content[0] <= i < n_content[1]
+        iden = n_identity[0] <= i < n_identity[1]
+        assert not cont or not iden
+        f = 10.0 if content_loss_on_lr else 1.0
+        if cont:
+            return 1.0 * f, "features"
+        if iden:
+            return 10.0 * f, "identity"
+        return 0, None
+
+    return loss_weight_adv_g, loss_weight_adv_d, loss_weight_cont
+
+
 @dataclass
 class StepConfig:
-    """Knobs of config.py that shape the step (config.py:38,49-54,136-164,186-188)."""
+    """Knobs of config.py that shape the step (config.py:24,38,49-54,124-166,186-188).  The three loss
+    weights are either constants or functions of the epoch as ``gen_losses`` returns them (then
+    ``loss_weight_cont(epoch)`` yields (weight, "features" | "identity" | None))."""
     lr: float = 1e-5
     betas: tuple = (0.9, 0.999)
     lr_decay_per_step: float = 1.0
-    loss_weight_adv_g: float = 5e-2
-    loss_weight_adv_d: float = 1.0
-    loss_weight_cont: float = 1.0
+    loss_weight_adv_g: object = 5e-2
+    loss_weight_adv_d: object = 1.0
+    loss_weight_cont: object = 1.0
+    content_loss_on_lr: bool = False    # "unsupervised" variant (train.py:41-50, 95-97)
     real_label: float = 1.0
     real_label_reduced: float = 0.9
     fake_label: float = 0.0
@@ -52,9 +90,24 @@ class SRGANTrainer:
         self.dis_list_old: List[torch.Tensor] = []
         self.iteration = 0
         self.grad_sync = grad_sync      # parallel.GradSync or None
-        self._graph = None
+        self._graph = None              # graph of the plain step (no replayed fakes, epoch-0 weights)
+        self._graphs = {}               # (replayed fakes, weights) -> (CUDAGraph, outputs)
         self._static = None
+        self._static_old = []           # static bf16 buffers the replayed fakes are copied into
+        self._pool = None
         self._side = None
+        self._zero = None
+
+    def weights(self, epoch: int = 0):
+        """(lw_adv_d, lw_adv_g, lw_cont, extractor kind) for ``epoch`` (config.py:136-164)."""
+        c = self.cfg
+
+        def val(w):
+            return w(epoch) if callable(w) else w
+        cont = val(c.loss_weight_cont)
+        if not isinstance(cont, tuple):
+            cont = (cont, "features" if cont else None)
+        return val(c.loss_weight_adv_d), val(c.loss_weight_adv_g), cont[0], cont[1]
 
     # -- losses (train.py:128-186) -----------------------------------------------------------
     def adversarial_loss_d(self, real, curr_fake, old_fakes):
@@ -75,7 +128,10 @@ class SRGANTrainer:
         err, d_g_z2 = ops.bce_loss(out, self.cfg.real_label)
         return d_g_z2, err
 
-    def content_loss_g(self, real, fake, feat_real=None):
+    def content_loss_g(self, real, fake, feat_real=None, kind="features"):
+        """train.py:183-186; ``kind`` "identity" = model_content_extractor.identity(): pixel MSE."""
+        if kind == "identity":
+            return ops.mse_loss(real, fake)
         a = self.extractor(real) if feat_real is None else feat_real
         b = self.extractor(fake)
         return ops.mse_loss(a, b)
@@ -86,60 +142,95 @@ class SRGANTrainer:
         return self._side
 
     # -- one iteration -----------------------------------------------------------------------
-    def step(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=()):
-        """img_hr: (B,3,H,H) fp32 in [-1,1]; img_lr: (B,3,H/s,H/s).  Returns device scalars."""
+    def step(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=(), epoch: int = 0, img_hr2=None):
+        """img_hr: (B,3,H,H) fp32 in [-1,1]; img_lr: (B,3,H/s,H/s).  Returns device scalars.
+        ``epoch`` selects the scheduled loss weights; a zero weight skips its branch exactly as
+        train.py:56-78, 85-102, 106-108 do.  ``img_hr2``: in ``content_loss_on_lr`` mode the HR batch of the
+        second dataset that the discriminator sees as "real" (train.py:41-50); the content loss is then
+        taken between ``img_lr`` and the re-downsampled fake (train.py:95-97)."""
+        from .utils import lr_from_hr
         c = self.cfg
+        lw_d, lw_g, lw_c, kind = self.weights(epoch)
         ops.begin_step(img_hr.device, track_weight_uses=c.async_weight_grads)
+        if self._zero is None or self._zero.device != img_hr.device:
+            self._zero = torch.zeros((), dtype=torch.float32, device=img_hr.device)
+        on_lr = c.content_loss_on_lr
+        real_d = img_hr2 if (on_lr and img_hr2 is not None) else img_hr
+        cont_real = img_lr if on_lr else img_hr
         # the content-loss features of the REAL batch depend on nothing else in the step: they run on a
         # side stream, filling the SMs that the small generator / discriminator kernels leave idle
         feat_real = side = None
-        if c.overlap_real_features and img_hr.is_cuda:
+        if lw_c and kind == "features" and c.overlap_real_features and img_hr.is_cuda:
             side = self._side_stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side), torch.no_grad():
-                feat_real = self.extractor(img_hr)
+                feat_real = self.extractor(cont_real)
         fake = self.net_g(img_lr)
-
-        self.net_d.zero_grad(set_to_none=True)
         curr_fake = fake.detach()
-        d_g_z1, d_x, err_d = self.adversarial_loss_d(img_hr, curr_fake, old_fakes)
-        err_d = err_d * c.loss_weight_adv_d
-        with ops.async_weight_grads(c.async_weight_grads):
-            err_d.backward()
-        if self.grad_sync is not None:
-            self.grad_sync.sync(self.opt_d)
-        self.opt_d.step()
+
+        d_g_z1 = d_x = d_g_z2 = self._zero
+        err_d = err_g_adv = err_g_cont = self._zero
+        if lw_d:
+            self.net_d.zero_grad(set_to_none=True)
+            d_g_z1, d_x, err_d = self.adversarial_loss_d(real_d, curr_fake, old_fakes)
+            err_d = err_d * lw_d
+            with ops.async_weight_grads(c.async_weight_grads):
+                err_d.backward()
+            if self.grad_sync is not None:
+                self.grad_sync.sync(self.opt_d)
+            self.opt_d.step()
 
         self.net_g.zero_grad(set_to_none=True)
-        d_g_z2, err_g_adv = self.adversarial_loss_g(fake)
-        err_g_adv = err_g_adv * c.loss_weight_adv_g
+        if lw_g:
+            d_g_z2, err_g_adv = self.adversarial_loss_g(fake)
+            err_g_adv = err_g_adv * lw_g
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
-        err_g_cont = self.content_loss_g(img_hr, fake, feat_real) * c.loss_weight_cont
-        with ops.async_weight_grads(c.async_weight_grads):
-            (err_g_adv + err_g_cont).backward()
-        if self.grad_sync is not None:
-            self.grad_sync.sync(self.opt_g)
-        self.opt_g.step()
+        if lw_c:
+            cont_fake = lr_from_hr(fake, tuple(img_lr.shape[-2:])) if on_lr else fake
+            err_g_cont = self.content_loss_g(cont_real, cont_fake, feat_real, kind) * lw_c
+        if lw_g or lw_c:
+            with ops.async_weight_grads(c.async_weight_grads):
+                (err_g_adv + err_g_cont).backward()
+            if self.grad_sync is not None:
+                self.grad_sync.sync(self.opt_g)
+            self.opt_g.step()
         return {"fake": curr_fake, "err_d": err_d.detach(), "err_g_adv": err_g_adv.detach(),
                 "err_g_cont": err_g_cont.detach(), "d_x": d_x, "d_g_z1": d_g_z1, "d_g_z2": d_g_z2}
 
-    def train_iteration(self, img_hr, img_lr):
-        """step() plus the reference's experience replay bookkeeping (train.py:59-71,144-146)."""
+    def _sample_old(self):
         import random
         c = self.cfg
-        old = []
-        if c.use_replay and self.dis_list_old:
-            k = int(len(self.dis_list_old) * c.dis_list_old_ratio)
-            old = [self.dis_list_old[i].float() for i in random.sample(range(len(self.dis_list_old)), k)]
-        out = self.step(img_hr, img_lr, old)
-        if c.use_replay and self.iteration % c.dis_list_old_freq == 0:
-            snap = out["fake"].to(torch.bfloat16)      # replay list kept on the GPU in bf16
+        if not (c.use_replay and self.dis_list_old):
+            return []
+        k = int(len(self.dis_list_old) * c.dis_list_old_ratio)          # train.py:145
+        return [self.dis_list_old[i] for i in random.sample(range(len(self.dis_list_old)), k)]
+
+    def _remember(self, fake):
+        import random
+        c = self.cfg
+        if c.use_replay and self.iteration % c.dis_list_old_freq == 0:   # train.py:66-71
+            snap = fake.to(torch.bfloat16)      # replay list kept on the GPU in bf16 (a clone: ``fake`` may be a static graph output)
+            if snap.data_ptr() == fake.data_ptr():
+                snap = snap.clone()
             if len(self.dis_list_old) == c.dis_list_old_len:
                 self.dis_list_old[random.randint(0, c.dis_list_old_len - 1)] = snap
             else:
                 self.dis_list_old.append(snap)
         self.iteration += 1
+
+    def train_iteration(self, img_hr, img_lr, epoch: int = 0, img_hr2=None, graph: bool = False):
+        """step() plus the reference's experience-replay bookkeeping (train.py:59-71,144-146).  With
+        ``graph=True`` the step is replayed from a CUDA graph captured for this number of replayed fakes
+        and this epoch's loss weights (captured on first use, see ``capture``), so that training past
+        iteration 100 - when int(len * 0.01) >= 1 old fake batches join every D update - stays on the
+        graph path."""
+        old = self._sample_old()
+        if graph:
+            out = self.replay(img_hr, img_lr, old_fakes=old, epoch=epoch, img_hr2=img_hr2)
+        else:
+            out = self.step(img_hr, img_lr, [o.float() for o in old], epoch=epoch, img_hr2=img_hr2)
+        self._remember(out["fake"])
         return out
 
     # -- checkpoint (same dictionary as utils._save, utils.py:107-114) -----------------------------
@@ -170,22 +261,45 @@ class SRGANTrainer:
         dev = next(self.net_g.parameters()).device
         self.dis_list_old = [t.to(dev).to(torch.bfloat16) for t in checkpoint.get("dis_list", [])]
         self._graph = None          # a captured graph holds the old optimizer buffers
+        self._graphs = {}
         return int(checkpoint.get("epoch", 0))
 
     # -- CUDA graph of the whole step ----------------------------------------------------------
-    def capture(self, img_hr: torch.Tensor, img_lr: torch.Tensor, warmup: int = 2):
-        """Capture ``step`` (no replayed fakes) into one CUDA graph with static input buffers."""
-        self._static = (img_hr.clone(), img_lr.clone())
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self.step(*self._static)
-        torch.cuda.current_stream().wait_stream(side)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._graph_out = self.step(*self._static)
-        return self._graph_out
+    def _graph_key(self, n_old, epoch):
+        return (n_old,) + tuple(self.weights(epoch))
+
+    def capture(self, img_hr: torch.Tensor, img_lr: torch.Tensor, warmup: int = 2, n_old: int = 0,
+                epoch: int = 0, img_hr2=None):
+        """Capture ``step`` into one CUDA graph with static input buffers: one graph per (number of
+        replayed fakes, loss weights of the epoch).  All graphs share one memory pool (they never run
+        concurrently) and the static inputs.  ``warmup`` eager steps run first (they ARE training steps);
+        the graphs for n_old > 0 are normally captured with warmup=0 by ``replay`` on first use."""
+        if self._static is None:
+            self._static = (img_hr.clone(), img_lr.clone(), img_hr.clone() if img_hr2 is None else img_hr2.clone())
+        while len(self._static_old) < n_old:
+            self._static_old.append(torch.zeros(self._static[0].shape, dtype=torch.bfloat16, device=img_hr.device))
+        hr2 = self._static[2] if self.cfg.content_loss_on_lr else None
+
+        def run():
+            return self.step(self._static[0], self._static[1], [o.float() for o in self._static_old[:n_old]],
+                             epoch=epoch, img_hr2=hr2)
+        if warmup:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    run()
+            torch.cuda.current_stream().wait_stream(side)
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self._pool):
+            out = run()
+        key = self._graph_key(n_old, epoch)
+        self._graphs[key] = (graph, out)
+        if key == self._graph_key(0, 0):
+            self._graph, self._graph_out = graph, out
+        return out
 
     def replay_from_feed(self, feed: "HostFeed"):
         """One captured step on the next batch of ``feed`` (pinned host HR patches): the LR input is
@@ -200,11 +314,22 @@ class SRGANTrainer:
         self._graph.replay()
         return self._graph_out
 
-    def replay(self, img_hr: torch.Tensor, img_lr: torch.Tensor):
+    def replay(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=(), epoch: int = 0, img_hr2=None):
+        """Replay the graph of this (number of replayed fakes, epoch weights); captured on first use."""
+        key = self._graph_key(len(old_fakes), epoch)
+        if key not in self._graphs:
+            if self._static is None:
+                raise RuntimeError("SRGANTrainer.replay: call capture() first")
+            self.capture(self._static[0], self._static[1], warmup=0, n_old=len(old_fakes), epoch=epoch)
+        graph, out = self._graphs[key]
         self._static[0].copy_(img_hr, non_blocking=True)
         self._static[1].copy_(img_lr, non_blocking=True)
-        self._graph.replay()
-        return self._graph_out
+        if img_hr2 is not None:
+            self._static[2].copy_(img_hr2, non_blocking=True)
+        for buf, o in zip(self._static_old, old_fakes):
+            buf.copy_(o, non_blocking=True)
+        graph.replay()
+        return out
 
 
 class HostFeed:

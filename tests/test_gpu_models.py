@@ -505,3 +505,88 @@ def test_host_feed_pipeline_matches_direct_replay(cuda, golden_dir):
     for i, (a, b) in enumerate(zip(res[0], res[1])):
         for x, y in zip(a, b):
             assert abs(x - y) <= (5e-3 if i == 0 else 2e-2) * abs(x) + 1e-6, (i, a, b)
+
+
+@pytest.mark.parametrize("case", ["on_lr", "no_adv", "adv_only", "identity_x10"])
+def test_step_branches_vs_reference_train_loop(cuda, golden_dir, case):
+    """The step's other branches - content_loss_on_lr (HR swap for D, identity content loss x100 on the
+    re-downsampled fake: the bicubic BACKWARD kernel is on the path), zero-weight skips, identity() x10 -
+    against the losses of the UNMODIFIED reference train_loop (golden, oracle/validate_against_reference.py)."""
+    import sisr_b200 as m
+    g = _load(golden_dir, "train_step_branches")
+    c = g["cases"][case]
+    wg, wd, wc, kind = c["weights"]
+    tr, _ = _build_step(m, g["seed"], g["shape"], g["features"], g["strides"], g["mask"], g["lr"])
+    tr.cfg.content_loss_on_lr = c["content_loss_on_lr"]
+    tr.cfg.loss_weight_adv_g = lambda e: wg
+    tr.cfg.loss_weight_adv_d = lambda e: wd
+    tr.cfg.loss_weight_cont = lambda e: (wc, kind)
+    d_before = {k: v.detach().clone() for k, v in tr.net_d.state_dict().items()}
+    for i in range(2):
+        hr = S.synthetic_hr(g["seed"] + 10 + i, g["B"], g["HR"])
+        hr2 = S.synthetic_hr(g["seed"] + 30 + i, g["B"], g["HR"]).cuda() if c["content_loss_on_lr"] else None
+        out = tr.step(hr.cuda(), O.lr_from_hr(hr, (g["LR"], g["LR"])).cuda(), img_hr2=hr2)
+        tol = 2e-2 if i == 0 else 5e-2
+        for key in ("err_d", "err_g_adv", "err_g_cont"):
+            want = c[key][i]
+            got = float(out[key])
+            if want == 0.0:
+                assert got == 0.0, (case, key, got)
+            else:
+                assert abs(got - want) < tol * abs(want), (case, i, key, got, want)
+    if not wd and not wg:
+        for k, v in tr.net_d.state_dict().items():
+            assert torch.equal(v, d_before[k]), k       # no D forward at all: buffers untouched too
+
+
+def test_gen_losses_schedule_matches_config():
+    """config.gen_losses (config.py:124-166) restated: defaults of both modes and windowed schedules."""
+    from sisr_b200.train import gen_losses
+    a, b, c = gen_losses(False)
+    assert (a(0), b(0), c(0)) == (5e-2, 1.0, (1.0, "features")) and a(10 ** 6) == 5e-2
+    a, b, c = gen_losses(True)
+    assert (a(0), b(0), c(0)) == (5e-3, 1.0, (100.0, "identity"))
+    a, b, c = gen_losses(False, n_g=(2, 5), n_d=(2, 5), n_content=(1, 9), n_identity=(0, 1))
+    assert [a(e) for e in range(6)] == [0, 0, 5e-2, 5e-2, 5e-2, 0]
+    assert [b(e) for e in (1, 2, 5)] == [0, 1.0, 0]
+    assert c(0) == (10.0, "identity") and c(1) == (1.0, "features") and c(9) == (0, None)
+
+
+def test_graph_replay_with_replayed_fakes(cuda, golden_dir):
+    """Training past iteration 100 stays on the CUDA-graph path: one graph per number k of replayed fakes
+    (train.py:144-146), captured on first use; the graph step equals the eager step on the same inputs and
+    train_iteration(graph=True) keeps the replay list and the iteration counter."""
+    import sisr_b200 as m
+    g = _load(golden_dir, "train_step2")
+    hr = S.synthetic_hr(g["seed"] + 50, g["B"], g["HR"])
+    lr_img = O.lr_from_hr(hr, (g["LR"], g["LR"]))
+    olds = [(S.synthetic_hr(g["seed"] + 60 + i, g["B"], g["HR"]) * 0.5).to(torch.bfloat16) for i in range(2)]
+    keys = ("err_d", "err_g_adv", "err_g_cont", "d_g_z1")
+    res = {}
+    for mode in ("eager", "graph"):
+        tr, _ = _build_step(m, g["seed"], g["shape"], g["features"], g["strides"], g["mask"], 1e-5)
+        if mode == "graph":
+            tr.capture(hr.cuda(), lr_img.cuda(), warmup=0)
+        outs = []
+        for k in (0, 2, 1, 2):
+            old = [o.cuda() for o in olds[:k]]
+            if mode == "graph":
+                o = tr.replay(hr.cuda(), lr_img.cuda(), old_fakes=old)
+            else:
+                o = tr.step(hr.cuda(), lr_img.cuda(), [t.float() for t in old])
+            outs.append([float(o[x]) for x in keys])
+        res[mode] = outs
+        if mode == "graph":
+            assert sorted(k[0] for k in tr._graphs) == [0, 1, 2]
+            tr.cfg.use_replay = True
+            tr.cfg.dis_list_old_ratio = 0.5
+            for i in range(4):
+                tr.train_iteration(hr.cuda(), lr_img.cuda(), graph=True)
+            assert tr.iteration == 4 and len(tr.dis_list_old) == 4
+            assert tr.dis_list_old[0].dtype == torch.bfloat16
+            assert tr.dis_list_old[0].data_ptr() != tr.dis_list_old[1].data_ptr()    # snapshots, not the static output
+    for a, b in zip(res["eager"], res["graph"]):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 5e-3 * abs(x) + 1e-6, (res["eager"], res["graph"])
+    # more replayed fakes -> larger summed D loss (their BCE terms are added, not averaged)
+    assert res["eager"][1][0] > res["eager"][0][0]

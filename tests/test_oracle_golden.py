@@ -107,6 +107,33 @@ def test_train_step_matches_reference_train_loop(golden_dir, n_steps):
             assert float(((d_st[k] - ref).abs() > 0.1 * g["lr"]).float().mean()) <= 5e-3, k
 
 
+@pytest.mark.parametrize("case", ["on_lr", "no_adv", "adv_only", "identity_x10"])
+def test_train_step_branches_match_reference_train_loop(golden_dir, case):
+    """content_loss_on_lr (train.py:41-50, 95-97), zero-weight skips (train.py:56,86,94,106) and identity()
+    x10 (config.py:156-163) against the losses of the unmodified reference train_loop."""
+    g = _load(golden_dir, "train_step_branches")
+    c = g["cases"][case]
+    wg, wd, wc, kind = c["weights"]
+    seed = g["seed"]
+    g_st = S.generator_state(seed, n_blocks=2, n_suffix=1)
+    d_st = S.discriminator_state(seed + 1, g["shape"], g["features"], g["strides"])
+    d_init = S.clone_state(d_st)
+    v_st = S.vgg_state(seed + 2, g["mask"])
+    og = O.AdamState(O.trainable_names(g_st), g["lr"])
+    od = O.AdamState(O.trainable_names(d_st), g["lr"])
+    for i in range(2):
+        hr = S.synthetic_hr(seed + 10 + i, g["B"], g["HR"])
+        hr2 = S.synthetic_hr(seed + 30 + i, g["B"], g["HR"]) if c["content_loss_on_lr"] else None
+        out = O.train_step(g_st, d_st, v_st, hr, O.lr_from_hr(hr, (g["LR"], g["LR"])), d_strides=g["strides"],
+                           vgg_mask=g["mask"], opt_g=og, opt_d=od, w_adv_g=wg, w_adv_d=wd, w_cont=wc,
+                           content_loss_on_lr=c["content_loss_on_lr"], hr2=hr2, cont_kind=kind or "features")
+        for key in ("err_d", "err_g_adv", "err_g_cont"):
+            want = c[key][i]
+            assert abs(out[key] - want) <= 5e-4 * abs(want), (case, i, key, out[key], want)
+    if not wd and not wg:
+        assert all(torch.equal(d_st[k], d_init[k]) for k in d_init)      # D untouched when its branches are off
+
+
 def test_bce_restatement_matches_torch():
     p = torch.tensor([1e-9, 0.3, 0.999999, 1.0, 0.0])
     for t in (0.0, 0.9, 1.0):
