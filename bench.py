@@ -201,11 +201,65 @@ def build_trainer(dev, batch, world, grad_sync=None):
         from sisr_b200 import parallel
         for net in (net_g, net_d, ext):
             parallel.broadcast_module(net)
-    tr = m.SRGANTrainer(net_g, net_d, ext, m.StepConfig(lr=1e-5, use_replay=False), grad_sync=grad_sync)
-    if grad_sync is not None:
-        grad_sync.attach(tr.opt_d)
-        grad_sync.attach(tr.opt_g)
-    return tr
+    # with a GradSync the trainer broadcasts weights + buffers and attaches both optimizers itself
+    return m.SRGANTrainer(net_g, net_d, ext, m.StepConfig(lr=1e-5, use_replay=False), grad_sync=grad_sync)
+
+
+DP_GOLDEN = os.path.join(ROOT, "profiles", "r2_dp_check_n1.json")
+
+
+def dp_check(dev, rank, world, tr_timed):
+    """Data-parallel correctness evidence carried by the bench line (all ranks call this):
+      * ``weights_identical``: after the timed steps every rank holds bit-identical G / D weights, BN running
+        statistics and spectral-norm vectors (an int64 checksum of the raw bits, all-gathered);
+      * ``losses``: ONE step of a fresh, identically seeded trainer on a fixed 64-patch global batch sharded
+        64/N per rank (SyncBN + gradient all-reduce => the single-process step on the whole batch), the three
+        losses averaged over ranks, compared with the committed N = 1 values (profiles/r2_dp_check_n1.json,
+        written by an N = 1 run of this same function) within 5e-3."""
+    import torch
+    import torch.distributed as dist
+    from sisr_b200 import parallel
+    import torch.nn.functional as F
+
+    def checksum(nets):
+        acc = torch.zeros((), dtype=torch.int64, device=dev)
+        for net in nets:
+            for t in list(net.parameters()) + list(net.buffers()):
+                if t.dtype == torch.float32:
+                    acc += t.detach().contiguous().view(torch.int32).to(torch.int64).sum()
+        return acc
+    mine = checksum((tr_timed.net_g, tr_timed.net_d)).reshape(1)
+    sums = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(sums, mine)
+    else:
+        sums = [mine]
+    identical = all(int(x) == int(sums[0]) for x in sums)
+    gs = parallel.GradSync() if world > 1 else None
+    tr = build_trainer(dev, 64 // world, world, gs)
+    gen = torch.Generator().manual_seed(4242)
+    hr_all = torch.rand((64, 3, 96, 96), generator=gen) * 2 - 1
+    lr_all = F.interpolate(hr_all, (24, 24), mode="bicubic", align_corners=True).clamp(-1, 1)
+    per = 64 // world
+    sl = slice(rank * per, (rank + 1) * per)
+    out = tr.step(hr_all[sl].to(dev), lr_all[sl].to(dev))
+    losses = torch.stack([out["err_d"].reshape(()), out["err_g_adv"].reshape(()), out["err_g_cont"].reshape(())])
+    if world > 1:
+        dist.all_reduce(losses)
+        losses /= world
+    losses = [float(x) for x in losses]
+    res = {"weights_identical": identical, "checksums": [int(x) for x in sums], "losses": losses,
+           "global_batch": 64, "per_rank": per}
+    if os.path.exists(DP_GOLDEN):
+        want = json.load(open(DP_GOLDEN))["losses"]
+        res["n1_losses"] = want
+        res["max_rel_diff_vs_n1"] = max(abs(a - b) / abs(b) for a, b in zip(losses, want))
+        res["losses_match_n1"] = res["max_rel_diff_vs_n1"] < 5e-3
+    if world == 1 and rank == 0 and os.environ.get("SISR_WRITE_DP_GOLDEN"):
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump({"losses": losses, "how": "bench.py dp_check at N=1: one step, fresh seeded trainer, fixed "
+                   "64-patch batch (seed 4242), lr 1e-5"}, open(os.path.join(ROOT, "gpurun_out", "r2_dp_check_n1.json"), "w"))
+    return res
 
 
 def _graph_time_us(launch, reps=12, replays=5):
@@ -508,6 +562,7 @@ def run_ours(args):
         if ms_pipe < ms_e2e:
             ms_e2e, e2e_mode = ms_pipe, "pipelined (HostFeed: H2D of batch i+1 overlaps step i)"
     clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
+    dp = dp_check(dev, rank, world, tr) if (world > 1 or os.environ.get("SISR_WRITE_DP_GOLDEN")) else None
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -535,6 +590,7 @@ def run_ours(args):
         "step_frac_of_sustained_bf16": FLOP_PER_PATCH * batch / (ms / args.steps * 1e-3) / 1e12
         / peaks["bf16_sustained"],
         "losses": [float(x) for x in losses],
+        "dp_check": dp,
         "clocks": clocks,
         "e2e": {"value": total_patches / (ms_e2e * 1e-3), "unit": "patches/s",
                 "h2d_bytes_per_step": hr_host.numel() * 4,

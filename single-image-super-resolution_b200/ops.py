@@ -157,16 +157,24 @@ def _wgrad_stream():
     return _async["stream"]
 
 
+_grad_ready_cb = [None]
+
+
+def set_grad_ready_callback(fn):
+    """``fn(param)`` is called whenever a side-stream weight gradient has been attached to ``param.grad``
+    (those gradients do not pass through autograd's accumulation, so its post-accumulate hooks never
+    see them).  parallel.GradSync registers itself here; None removes the callback."""
+    _grad_ready_cb[0] = fn
+
+
 def _deliver(entry):
     weight, bias, dw, db, want_w, want_b = entry
     for p, g, want in ((weight, dw, want_w), (bias, db, want_b)):
         if not want or p is None:
             continue
         p.grad = g if p.grad is None else p.grad + g
-        hooks = getattr(p, "_post_accumulate_grad_hooks", None)
-        if hooks:
-            for hook in list(hooks.values()):
-                hook(p)
+        if _grad_ready_cb[0] is not None:
+            _grad_ready_cb[0](p)
 
 
 def _deliver_ready(keep_last: int):
@@ -206,6 +214,22 @@ def async_weight_grads(on: bool = True):
         _async["on"] = prev
 
 
+_sync_scope = [False]
+
+
+@contextlib.contextmanager
+def sync_bn_scope():
+    """SyncBN statistics are exchanged only inside this scope, which the trainer opens around a step that
+    EVERY rank executes.  A forward pass outside it (one rank rendering a preview in train mode, as the
+    reference's save_curr_vis does, utils.py:53-56) normalises with local statistics instead of
+    desynchronising the per-slot epochs of the peer exchange - which used to end in a 10 s spin and a trap."""
+    prev, _sync_scope[0] = _sync_scope[0], True
+    try:
+        yield
+    finally:
+        _sync_scope[0] = prev
+
+
 def begin_step(device=None, track_weight_uses: bool = False):
     """Called by the trainer at the start of every step (all ranks): resets per-step numbering and
     re-zeroes the accumulator arena."""
@@ -223,7 +247,7 @@ def begin_step(device=None, track_weight_uses: bool = False):
 
 def _world():
     import torch.distributed as dist
-    if _dist_group is None or not dist.is_initialized():
+    if _dist_group is None or not _sync_scope[0] or not dist.is_initialized():
         return 1
     return dist.get_world_size(_dist_group)
 

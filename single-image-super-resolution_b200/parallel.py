@@ -71,7 +71,10 @@ class PeerExchange:
 
     def next_slot(self) -> int:
         s = self.slot
-        self.slot = (s + 1) % self.SLOTS
+        if s >= self.SLOTS:
+            raise RuntimeError(f"PeerExchange: more than {self.SLOTS} SyncBN exchanges in one step (a slot "
+                               "would be reused before its epoch advanced); call ops.begin_step() per step")
+        self.slot = s + 1
         return s
 
     def reset(self):
@@ -102,9 +105,23 @@ class GradSync:
         self.bucket_bytes = bucket_bytes
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._plans: Dict[int, dict] = {}
+        self._hooks: Dict[torch.nn.Parameter, object] = {}
         self.comm_stream = None
 
-    def attach(self, optimizer):
+    def grad_ready(self, param):
+        """Public entry for gradients that bypass autograd's accumulation (ops.set_grad_ready_callback)."""
+        hook = self._hooks.get(param)
+        if hook is not None:
+            hook(param)
+
+    def attach(self, optimizer, module: torch.nn.Module = None, src: int = 0):
+        """Register the optimizer's parameters for bucketed reduction.  With ``module`` the replicas are
+        first made identical: its parameters AND buffers (spectral-norm u/v, BN running statistics) are
+        broadcast from rank ``src``.  Idempotent per optimizer."""
+        if module is not None:
+            broadcast_module(module, src)
+        if id(optimizer) in self._plans:
+            return
         params = [p for g in optimizer.param_groups for p in g["params"] if p.requires_grad]
         if not params:
             return
@@ -132,7 +149,10 @@ class GradSync:
             plan["buckets"].append({"params": bl, "flat": flat, "ready": 0})
         self._plans[id(optimizer)] = plan
         for p in params:
-            p.register_post_accumulate_grad_hook(self._make_hook(plan, p))
+            hook = self._make_hook(plan, p)
+            self._hooks[p] = hook
+            p.register_post_accumulate_grad_hook(hook)     # gradients that autograd accumulates
+        ops.set_grad_ready_callback(self.grad_ready)       # gradients delivered from the wgrad side stream
         optimizer.grad_views = plan["views"]
         optimizer.grad_scale = 1.0 / self.world
 

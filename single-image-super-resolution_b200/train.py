@@ -90,6 +90,13 @@ class SRGANTrainer:
         self.dis_list_old: List[torch.Tensor] = []
         self.iteration = 0
         self.grad_sync = grad_sync      # parallel.GradSync or None
+        if grad_sync is not None:
+            # replicas start identical (weights, spectral-norm vectors, BN statistics) and both optimizers
+            # reduce their gradients through the bucketed all-reduce
+            from .parallel import broadcast_module
+            broadcast_module(extractor)
+            grad_sync.attach(self.opt_d, net_d)
+            grad_sync.attach(self.opt_g, net_g)
         self._graph = None              # graph of the plain step (no replayed fakes, epoch-0 weights)
         self._graphs = {}               # (replayed fakes, weights) -> (CUDAGraph, outputs)
         self._static = None
@@ -143,6 +150,12 @@ class SRGANTrainer:
 
     # -- one iteration -----------------------------------------------------------------------
     def step(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=(), epoch: int = 0, img_hr2=None):
+        """One training iteration; every rank of a data-parallel run must call it (SyncBN statistics are
+        exchanged only inside, see ops.sync_bn_scope).  Arguments: see ``_step``."""
+        with ops.sync_bn_scope():
+            return self._step(img_hr, img_lr, old_fakes, epoch, img_hr2)
+
+    def _step(self, img_hr, img_lr, old_fakes=(), epoch: int = 0, img_hr2=None):
         """img_hr: (B,3,H,H) fp32 in [-1,1]; img_lr: (B,3,H/s,H/s).  Returns device scalars.
         ``epoch`` selects the scheduled loss weights; a zero weight skips its branch exactly as
         train.py:56-78, 85-102, 106-108 do.  ``img_hr2``: in ``content_loss_on_lr`` mode the HR batch of the

@@ -27,7 +27,10 @@ def _worker(rank, world, port, ret):
     assert (r, w) == (rank, world)
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
-    parallel.broadcast_module(net)
+    if rank == 1:                                     # replicas start different ...
+        with torch.no_grad():
+            for p_ in net.parameters():
+                p_.add_(1.0)
 
     class FakeOpt:
         def __init__(self, params):
@@ -35,7 +38,13 @@ def _worker(rank, world, port, ret):
             self.grad_views, self.grad_scale = None, 1.0
     opt = FakeOpt(net.parameters())
     sync = parallel.GradSync(bucket_bytes=300)       # several buckets
-    sync.attach(opt)
+    sync.attach(opt, net)                            # ... attach(module=...) broadcasts rank 0's weights
+    sync.attach(opt, net)                            # idempotent: no second set of hooks
+    w0 = [p_.detach().clone() for p_ in net.parameters()]
+    same = [[torch.zeros_like(t) for _ in range(world)] for t in w0]
+    for t, out in zip(w0, same):
+        dist.all_gather(out, t)
+    assert all(torch.equal(o[0], o[1]) for o in same)
     torch.manual_seed(100 + rank)
     x = torch.randn(5, 8)
     net(x).pow(2).sum().backward()
@@ -50,7 +59,13 @@ def _worker(rank, world, port, ret):
     # SyncBN reduction helper
     t = torch.full((4,), float(rank + 1))
     ops._all_reduce(t)
-    ok = ok and ops._world() == world and torch.equal(t, torch.full((4,), 3.0))
+    ok = ok and torch.equal(t, torch.full((4,), 3.0))
+    # SyncBN is opt-in per step: outside the trainer's scope a BN forward uses local statistics
+    ok = ok and ops._world() == 1
+    with ops.sync_bn_scope():
+        ok = ok and ops._world() == world
+    # gradients that bypass autograd reach the buckets through the public callback
+    ok = ok and ops._grad_ready_cb[0] is not None and ops._grad_ready_cb[0].__self__ is sync
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

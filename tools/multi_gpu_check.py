@@ -24,11 +24,7 @@ def build(dev, grad_sync, seed=800, shape=(3, 32, 32), feats=(64, 64, 128, 128),
     for net, st in ((net_g, g_st), (net_d, d_st), (ext, v_st)):
         torch.nn.Module.load_state_dict(net, S.clone_state(st), strict=True)
     net_g, net_d, ext = net_g.to(dev), net_d.to(dev), ext.to(dev)
-    tr = m.SRGANTrainer(net_g, net_d, ext, m.StepConfig(lr=1e-5, use_replay=False), grad_sync=grad_sync)
-    if grad_sync is not None:
-        grad_sync.attach(tr.opt_d)
-        grad_sync.attach(tr.opt_g)
-    return tr
+    return m.SRGANTrainer(net_g, net_d, ext, m.StepConfig(lr=1e-5, use_replay=False), grad_sync=grad_sync)
 
 
 def main():
