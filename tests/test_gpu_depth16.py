@@ -176,9 +176,8 @@ def test_config2_shaped_step_vs_oracle(cuda):
     hr = S.synthetic_hr(seed + 5, 4, 96)
     lr_img = O.lr_from_hr(hr, (24, 24))
     out = tr.step(hr.cuda(), lr_img.cuda())
-    ref = O.train_step(g_st, d_st, v_st, hr, lr_img, d_strides=STRIDES, vgg_mask=0b10000,
-                       opt_g=O.AdamState(O.trainable_names(g_st), lr),
-                       opt_d=O.AdamState(O.trainable_names(d_st), lr))
+    og, od = O.AdamState(O.trainable_names(g_st), lr), O.AdamState(O.trainable_names(d_st), lr)
+    ref = O.train_step(g_st, d_st, v_st, hr, lr_img, d_strides=STRIDES, vgg_mask=0b10000, opt_g=og, opt_d=od)
     psnr = O.psnr(out["fake"].float().cpu(), ref["fake"])
     print(f"config-2 shape, B=4: PSNR {psnr:.1f} dB; " +
           "; ".join(f"{k} {float(out[k]):.5f} (oracle {ref[k]:.5f})" for k in ("err_d", "err_g_adv", "err_g_cont")))
@@ -189,11 +188,11 @@ def test_config2_shaped_step_vs_oracle(cuda):
     hr2 = S.synthetic_hr(seed + 6, 4, 96)
     lr2 = O.lr_from_hr(hr2, (24, 24))
     out2 = tr.step(hr2.cuda(), lr2.cuda())
-    ref2 = O.train_step(g_st, d_st, v_st, hr2, lr2, d_strides=STRIDES, vgg_mask=0b10000,
-                        opt_g=O.AdamState(O.trainable_names(g_st), lr),
-                        opt_d=O.AdamState(O.trainable_names(d_st), lr))
+    ref2 = O.train_step(g_st, d_st, v_st, hr2, lr2, d_strides=STRIDES, vgg_mask=0b10000, opt_g=og, opt_d=od)
+    print("step 2: " + "; ".join(f"{k} {float(out2[k]):.5f} (oracle {ref2[k]:.5f})"
+                                 for k in ("err_d", "err_g_adv", "err_g_cont")))
     for k in ("err_d", "err_g_adv", "err_g_cont"):
-        assert abs(float(out2[k]) - ref2[k]) < 5e-2 * abs(ref2[k]), (k, float(out2[k]), ref2[k])
+        assert abs(float(out2[k]) - ref2[k]) < 2e-2 * abs(ref2[k]), (k, float(out2[k]), ref2[k])
 
 
 def test_frozen_trunk_step_vs_oracle(cuda):
