@@ -30,6 +30,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_PATCH = 42.55e9          # 3 F_G + 8 F_D + 3 F_V at 96x96
+# BASELINE.json configs[1] / [3] / [4]: algorithmic GFLOP per HR patch of the full step
+CONFIGS = {
+    "x4": {"hr": 96, "lr": 24, "n_suffix": 1, "frozen": False, "flop": 42.55e9, "batch": 64,
+           "workload": "SRGAN x4 full training step (G 16 blocks + suffix, D @3x96x96, MaskedVGG54 content loss "
+                       "+ adversarial loss), 96x96 HR patches"},
+    "frozen": {"hr": 96, "lr": 24, "n_suffix": 1, "frozen": True, "flop": 38.66e9, "batch": 64,
+               "workload": "progressive x4 = x2 generator wrapped by GeneratorSuffix(freeze_prefix, freeze_upscale, "
+                           "freeze_end) (config.py:96): frozen 16-block trunk, spectral norm in G and D, D @3x96x96, "
+                           "MaskedVGG54, 96x96 HR patches"},
+    "x8": {"hr": 256, "lr": 32, "n_suffix": 2, "frozen": False, "flop": 280.75e9, "batch": 16,
+           "workload": "progressive x8 supervised SRGAN: GeneratorSuffix(GeneratorSuffix(Generator)), 32x32 LR -> "
+                       "256x256 HR patches, 256-channel pre-upsample maps, D @3x256x256 (138.9 M parameters), "
+                       "MaskedVGG54"},
+}
 D_FEATS = [64, 64, 128, 128, 256, 256, 512, 512]
 D_STRIDES = [1, 2, 1, 2, 1, 2, 1, 2]
 VGG54 = 0b10000
@@ -53,7 +67,7 @@ class ClockSampler:
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_power_cap,power.draw")
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
@@ -72,14 +86,20 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        return self.window(t0, t1)
+
+    def window(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         rows = [s for (t, s) in self.samples if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.2)]
         sm = sorted(int(s[0]) for s in rows if s and s[0].isdigit())
         mx = [int(s[1]) for (_, s) in self.samples if len(s) > 1 and s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in rows if len(s) >= 6
                           for i in range(4) if s[2 + i].lower().startswith("active")})
+        pw = sorted(float(s[6]) for s in rows if len(s) >= 7 and s[6].replace(".", "", 1).isdigit())
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None}
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
@@ -158,7 +178,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = args.batch
+    batch = args.batch or 64
     got = reference_train_loop_time(batch, args.steps, args.warmup, threads)
     if got is not None:
         sec, steps = got
@@ -190,12 +210,20 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------ our arm
-def build_trainer(dev, batch, world, grad_sync=None):
+def build_trainer(dev, batch, world, grad_sync=None, config="x4"):
     import torch
     import sisr_b200 as m
+    cfg = CONFIGS[config]
     torch.manual_seed(0)
-    net_g = m.GeneratorSuffix(m.Generator(16, 64, 256, [2], use_sn=True)).to(dev)
-    net_d = m.Discriminator((3, 96, 96), D_FEATS, D_STRIDES).to(dev)
+    net_g = m.Generator(16, 64, 256, [2], use_sn=True)
+    for i in range(cfg["n_suffix"]):
+        last = i == cfg["n_suffix"] - 1
+        if cfg["frozen"] and last:
+            net_g = m.GeneratorSuffix(net_g, freeze_prefix=True, freeze_upscale=True, freeze_end=True)
+        else:
+            net_g = m.GeneratorSuffix(net_g)
+    net_g = net_g.to(dev)
+    net_d = m.Discriminator((3, cfg["hr"], cfg["hr"]), D_FEATS, D_STRIDES).to(dev)
     ext = m.MaskedVGG(VGG54).to(dev)
     if world > 1:
         from sisr_b200 import parallel
@@ -340,7 +368,7 @@ def time_conv_dgrad(dev, n, h, cin, cout, stride=1, ps=0):
             "ms": us * 1e-3, "tflops": flops / (us * 1e-6) / 1e12}
 
 
-def time_dominant_kernel(dev, batch):
+def time_dominant_kernel(dev, batch, frozen=False):
     """igemm_t_kernel (18.6 % of the step's kernel time, profiles/r1_step_launches_b64_final.csv) over
     ALL of its 93 launches per step: every distinct (shape, direction) it serves is timed and weighted by
     its launch count; achieved = sum of algorithmic FLOPs / sum of launch durations."""
@@ -378,6 +406,8 @@ def time_dominant_kernel(dev, batch):
         (3, fwd(96, 64, 64, True, 2)), (3, fwd(48, 128, 128, True, 2)),
         (2, time_conv_dgrad(dev, batch, 48, 64, 256, 1, 2)),
     ]
+    if frozen:       # frozen trunk (configs[3]): no data gradient below the suffix conv
+        parts = [pm for pm in parts if not pm[1]["kernel"].startswith("dgrad of conv3x3 64->64 s1 @24")]
     flops = sum(c * m["flops"] for c, m in parts)
     ms = sum(c * m["ms"] for c, m in parts)
     launches = sum(c for c, _ in parts)
@@ -420,6 +450,27 @@ def time_hbm_kernels(dev, batch):
     return out
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel's most frequent class
+    (trunk conv), parsed from the newest committed `ncu --set full` summary under profiles/ (null if none)."""
+    import glob
+    import re
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_trunk_conv*.txt")), reverse=True):
+        rd = wr = None
+        for ln in open(path):
+            m = re.search(r"dram__bytes_(read|write)\.sum\s+([0-9.,]+)\s+(\w+)", ln)
+            if m:
+                val = float(m.group(2).replace(",", "")) * unit.get(m.group(3), 1.0)
+                if m.group(1) == "read" and rd is None:
+                    rd = val
+                elif m.group(1) == "write" and wr is None:
+                    wr = val
+            if rd is not None and wr is not None:
+                return {"bytes": int(rd + wr), "source": os.path.relpath(path, ROOT)}
+    return {"bytes": None, "source": None}
+
+
 def dominant_share():
     """igemm_t_kernel's share of the step's kernel time, read from the committed ncu launch-list summary."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_step_launches_b64_final_summary.txt")
@@ -446,7 +497,9 @@ def run_ours(args):
         sampler.start()                 # nvidia-smi needs ~1 s to start; samples are windowed later
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    batch = args.batch
+    cfg = CONFIGS[args.config]
+    batch = args.batch or cfg["batch"]
+    HR, LRS = cfg["hr"], cfg["lr"]
     use_graph = not args.no_graph      # NCCL all-reduces and the peer-memory SyncBN kernels are captured too
     bucket = int(os.environ.get("SISR_BUCKET_MB", "0")) << 20
     gs = (parallel.GradSync(bucket_bytes=bucket) if bucket else parallel.GradSync()) \
@@ -454,11 +507,11 @@ def run_ours(args):
     if os.environ.get("SISR_DIAG_NO_SYNCBN"):      # attribution experiments only (results differ from the spec)
         from sisr_b200 import ops as _ops
         _ops.set_sync_group(None)
-    tr = build_trainer(dev, batch, world, gs)
+    tr = build_trainer(dev, batch, world, gs, args.config)
     gen = torch.Generator().manual_seed(1234 + rank)          # synthetic HR patches ~ U[-1, 1]
-    hr_host = (torch.rand((batch, 3, 96, 96), generator=gen) * 2 - 1).pin_memory()
+    hr_host = (torch.rand((batch, 3, HR, HR), generator=gen) * 2 - 1).pin_memory()
     import torch.nn.functional as F
-    lr_host = F.interpolate(hr_host, (24, 24), mode="bicubic", align_corners=True).clamp(-1, 1).pin_memory()
+    lr_host = F.interpolate(hr_host, (LRS, LRS), mode="bicubic", align_corners=True).clamp(-1, 1).pin_memory()
     hr, lr = hr_host.to(dev), lr_host.to(dev)
 
     def barrier():
@@ -541,7 +594,7 @@ def run_ours(args):
         losses = None
         for _ in range(args.steps):
             hr.copy_(hr_host, non_blocking=True)
-            lr.copy_(lr_from_hr(hr, (24, 24)))
+            lr.copy_(lr_from_hr(hr, (LRS, LRS)))
             o = step()
             losses = loss_vec(o).cpu()                                     # D2H + sync
         return losses
@@ -566,17 +619,52 @@ def run_ours(args):
         ms_pipe, losses = timed_e2e(e2e_pipelined)
         if ms_pipe < ms_e2e:
             ms_e2e, e2e_mode = ms_pipe, "pipelined (HostFeed: H2D of batch i+1 overlaps step i)"
-    clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
+    clocks = sampler.window(wall0, time.time()) if rank == 0 else None
+    # ---- sustained leg: the driver-dictated K steps last ~0.2 s (burst clocks); the same loop for >= S seconds
+    # shows what the step costs once the part sits at its power cap
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds / (ms / args.steps * 1e-3)) + 1)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ws0 = time.time()
+        s0.record()
+        for _ in range(n_sus):
+            step()
+        s1.record()
+        barrier()
+        ws1 = time.time()
+        t_ = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ms_sus = float(t_) / n_sus
+        sustained = {"seconds": float(t_) * 1e-3, "steps": n_sus, "ms_per_step": ms_sus,
+                     "value": batch * world / (ms_sus * 1e-3), "unit": "patches/s",
+                     "clocks": sampler.window(ws0 + 1.0, ws1) if rank == 0 else None}
+    if rank == 0:
+        sampler.stop()
     dp = dp_check(dev, rank, world, tr) if (world > 1 or os.environ.get("SISR_WRITE_DP_GOLDEN")) else None
     if rank != 0:
         if world > 1:
             dist.barrier()
         return
     peaks = measured_peaks()
-    dom = time_dominant_kernel(dev, batch)
-    others = [time_conv_kernel(dev, batch, 96, 64, 64, False), time_conv_kernel(dev, batch, 48, 128, 128, False),
-              time_conv_kernel(dev, batch, 24, 256, 256, False), time_conv_kernel(dev, batch, 12, 512, 512, False)]
-    hbm = time_hbm_kernels(dev, batch)
+    traffic = ncu_traffic()
+    if args.config == "x8":
+        # the FLOP-heaviest conv class of the 256x256 step (VGG conv3_x: 256 -> 256 @64x64, 10 launches per step)
+        dom = time_conv_kernel(dev, batch, 64, 256, 256, False)
+        dom["classes"] = [{"launches": 10, "kernel": dom["kernel"], "us": dom["ms"] * 1e3, "tflops": dom["tflops"]}]
+        dom["kernel"] = "igemm_tc_kernel<256,4>: " + dom["kernel"]
+        traffic = {"bytes": None, "source": None}
+        others = [time_conv_kernel(dev, batch, 256, 64, 64, False), time_conv_kernel(dev, batch, 128, 128, 128, False),
+                  time_conv_kernel(dev, batch, 32, 512, 512, False)]
+        hbm = []
+    else:
+        dom = time_dominant_kernel(dev, batch, frozen=cfg["frozen"])
+        dom["kernel"] = "igemm_t_kernel / igemm_th_kernel: " + dom["kernel"]
+        others = [time_conv_kernel(dev, batch, 96, 64, 64, False), time_conv_kernel(dev, batch, 48, 128, 128, False),
+                  time_conv_kernel(dev, batch, 24, 256, 256, False), time_conv_kernel(dev, batch, 12, 512, 512, False)]
+        hbm = time_hbm_kernels(dev, batch)
     total_patches = batch * world * args.steps
     value = total_patches / (ms * 1e-3)
     line = {
@@ -585,15 +673,16 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "ms_per_step_by_rank": ms_by_rank,
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "SRGAN x4 full training step (G 16 blocks + suffix, D @3x96x96, "
-                               "MaskedVGG54 content loss + adversarial loss), 96x96 HR patches",
+        "config": {"workload": cfg["workload"], "name": args.config,
                    "batch_per_gpu": batch, "global_batch": batch * world, "spectral_norm": True,
                    "parallelism": f"dp{world}" + (" + SyncBN" if world > 1 else ""),
                    "cuda_graph": use_graph,
                    "l2": "one step streams > 1 GB of activations/weights (> 126 MB L2) between reuses"},
-        "step_tflops": FLOP_PER_PATCH * batch / (ms / args.steps * 1e-3) / 1e12,
-        "step_frac_of_sustained_bf16": FLOP_PER_PATCH * batch / (ms / args.steps * 1e-3) / 1e12
+        "flop_per_patch": cfg["flop"],
+        "step_tflops": cfg["flop"] * batch / (ms / args.steps * 1e-3) / 1e12,
+        "step_frac_of_sustained_bf16": cfg["flop"] * batch / (ms / args.steps * 1e-3) / 1e12
         / peaks["bf16_sustained"],
+        "sustained": sustained,
         "losses": [float(x) for x in losses],
         "dp_check": dp,
         "clocks": clocks,
@@ -608,8 +697,8 @@ def run_ours(args):
                      # dram__bytes_read + write of one launch of the most frequent class (trunk conv), ncu
                      # --set full (profiles/r1_ncu_trunk_conv.txt): 4.83 MB read (the input activation,
                      # cold), 0 written back (the output stays in L2)
-                     "traffic": 4831488,
-                     "kernel": "igemm_t_kernel: " + dom["kernel"], "ms_per_launch": dom["ms"],
+                     "traffic": traffic["bytes"], "traffic_source": traffic["source"],
+                     "kernel": dom["kernel"], "ms_per_launch": dom["ms"],
                      "flops_per_launch": dom["flops"], "classes": dom["classes"],
                      "peak_source": peaks["source"] + " (burst: kernel timed alone)",
                      "share_of_step": dominant_share(),
@@ -647,7 +736,10 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=None, help="patches per GPU (default: the config's)")
+    ap.add_argument("--config", default="x4", choices=sorted(CONFIGS),
+                    help="x4 = BASELINE.json configs[1]/[2]; frozen = configs[3]; x8 = configs[4]")
+    ap.add_argument("--sustained-seconds", type=float, default=5.0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -53,6 +53,9 @@ int sisr_debug_transposed(int on);
 int sisr_debug_pair_mode(int on);
 /* debug / A-B timing: 0 = weight gradients always use the im2col-fed kernel (never the halo boxes) */
 int sisr_debug_wgrad_halo(int on);
+/* debug / A-B timing: 0 = the 64 -> 64 channel stride-1 layers (generator trunk, model_generator.py:10,13,39)
+ * do not use the transposed halo-fed kernel with stacked filter taps (csrc/igemm_th.cu); default 1 */
+int sisr_debug_th_mode(int on);
 /* 1 if the tcgen05 implicit-GEMM engine takes this fprop/dgrad shape, 0 if the CUDA-core kernel does */
 int sisr_conv_uses_tensor_cores(const sisr_conv_desc* d);
 

@@ -320,6 +320,41 @@ int main(int argc, char** argv) {
       {"c256_512_6x6_n8", 8, 6, 6, 256, 512, 1, 0, ACT_RELU, 0},
       {"c128_256_s2_12x12_n8", 8, 12, 12, 128, 256, 2, 0, ACT_NONE, 1},
   };
+  if (argc > 1 && argv[1][0] == 't') {
+    // transposed halo-fed kernel with stacked taps (igemm_th.cu), 64 -> 64 channels: "harness_igemm th"
+    igemm_set_halo_mode(0);
+    igemm_set_transposed(1);
+    igemm_set_th(1);
+    printf("-- transposed halo kernel, stacked taps (64 -> 64)\n");
+    const ConvCase th_cases[] = {
+        {"t_c64_24x24_n4", 4, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
+        {"t_c64_12x12_n3", 3, 12, 12, 64, 64, 1, 0, ACT_PRELU, 1},
+        {"t_c64_9x7_n2_odd", 2, 9, 7, 64, 64, 1, 0, ACT_LEAKY, 1},
+        {"t_c64_48x48_n2", 2, 48, 48, 64, 64, 1, 0, ACT_NONE, 1},
+        {"t_c64_96x96_n3", 3, 96, 96, 64, 64, 1, 0, ACT_RELU, 0},
+        {"t_c64_24x24_n150_multi", 150, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
+        {"t_c64_5x40_n7", 7, 5, 40, 64, 64, 1, 0, ACT_NONE, 1},
+    };
+    for (const auto& cc : th_cases) {
+      IgemmProblem q;
+      fill_fprop_problem(q, cc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+      if (!igemm_th_supported(q)) {
+        printf("[conv %s] NOT routed to the th kernel\n", cc.name);
+        ++fails;
+      }
+      fails += run_conv(cc, false);
+    }
+    const ConvCase th_big[] = {
+        {"trunk_c64_24x24_n64", 64, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
+        {"vgg_c64_96x96_n64", 64, 96, 96, 64, 64, 1, 0, ACT_RELU, 0},
+    };
+    for (const auto& cc : th_big) fails += run_conv(cc, true);
+    igemm_set_th(0);
+    for (const auto& cc : th_big) fails += run_conv(cc, true);      // same shapes on the im2col-fed transposed kernel
+    printf("harness: %d failure(s)\n", fails);
+    return fails ? 1 : 0;
+  }
+  igemm_set_th(0);
   igemm_set_halo_mode(0);
   igemm_set_transposed(1);
   printf("-- default engine (transposed tiles for Cout <= 128)\n");

@@ -1154,6 +1154,11 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
              p.Cout, p.num_taps, p.ldc);
     return 1;
   }
+  if (g_halo_mode != 2 && igemm_th_supported(p)) {
+    const int rc = igemm_th_launch(p, stream);
+    if (rc) snprintf(g_err, sizeof g_err, "%s", igemm_th_last_error());
+    return rc;
+  }
   const bool flat_out = p.osy == 1 && p.osx == 1 && p.opy == 0 && p.opx == 0 && p.OH == p.GH && p.OW == p.GW;
   if (g_transposed && p.Cout <= 128 && p.ps_c == 0 && flat_out && p.n_classes <= 1 && g_halo_mode != 2) {
     CUtensorMap tpx, tw;
