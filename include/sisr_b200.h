@@ -208,6 +208,12 @@ int sisr_mse_fwd(const float* a, const float* b, long long n, float coef, float*
 int sisr_mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
                  float* gb, void* stream);
 
+/* ---- image-quality metrics: PSNR and SSIM (11 x 11 Gaussian window, sigma 1.5, K1 0.01, K2 0.03) per image
+ *      of two NCHW fp32 batches with dynamic range `range` (2 for [-1, 1]).  The reference lists them as a todo
+ *      (README.md:88) for its viewer flow (visualisation.py:46-52).  workspace: 2 * n floats. ---- */
+int sisr_psnr_ssim(const float* a, const float* b, int n, int c, int h, int w, float range, float* workspace,
+                   float* psnr, float* ssim, void* stream);
+
 /* ---- data parallelism: replaces nn.DataParallel (config.py:114-118).  Gradient all-reduce is NCCL (host
  *      side, parallel.py); the per-layer SyncBN statistic exchange runs over NVLink peer memory:
  *      every rank allocates one workspace (sisr_peer_alloc), publishes its CUDA-IPC handle, maps the

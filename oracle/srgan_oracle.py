@@ -499,3 +499,28 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
 def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 2.0) -> float:
     mse = float(((a.double() - b.double()) ** 2).mean())
     return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)
+
+
+def ssim(a: torch.Tensor, b: torch.Tensor, data_range: float = 2.0) -> torch.Tensor:
+    """Per-image SSIM (Wang et al. 2004) of NCHW batches: 11 x 11 Gaussian window (sigma 1.5), K1 = 0.01,
+    K2 = 0.03, valid window positions only, mean over channels and positions.  The reference has no
+    implementation (README.md:88 lists PSNR / SSIM as a todo); this is the published definition."""
+    a, b = a.double(), b.double()
+    n, c, _, _ = a.shape
+    x = torch.arange(11, dtype=torch.float64) - 5.0
+    g = torch.exp(-x * x / (2 * 1.5 * 1.5))
+    g = g / g.sum()
+    win = (g[:, None] * g[None, :]).expand(c, 1, 11, 11)
+
+    def blur(t):
+        return F.conv2d(t, win, groups=c)
+    ma, mb = blur(a), blur(b)
+    va, vb, cov = blur(a * a) - ma * ma, blur(b * b) - mb * mb, blur(a * b) - ma * mb
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    s = ((2 * ma * mb + c1) * (2 * cov + c2)) / ((ma * ma + mb * mb + c1) * (va + vb + c2))
+    return s.reshape(n, -1).mean(dim=1)
+
+
+def psnr_per_image(a: torch.Tensor, b: torch.Tensor, data_range: float = 2.0) -> torch.Tensor:
+    mse = ((a.double() - b.double()) ** 2).reshape(a.shape[0], -1).mean(dim=1)
+    return 10.0 * torch.log10(data_range * data_range / mse)

@@ -12,6 +12,7 @@ from .model_generator import Generator, GeneratorSuffix
 from .optim import Adam
 from .train import SRGANTrainer, StepConfig
 from .utils import lr_from_hr
+from .metrics import evaluate, psnr_ssim
 
 __all__ = ["Generator", "GeneratorSuffix", "Discriminator", "MaskedVGG", "identity", "Adam",
-           "SRGANTrainer", "StepConfig", "lr_from_hr"]
+           "SRGANTrainer", "StepConfig", "lr_from_hr", "psnr_ssim", "evaluate"]

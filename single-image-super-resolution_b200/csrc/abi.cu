@@ -11,6 +11,7 @@
 #include "elementwise.h"
 #include "igemm.h"
 #include "linear.h"
+#include "metrics.h"
 #include "optim.h"
 #include "peer.h"
 #include "spectral.h"
@@ -470,6 +471,14 @@ int sisr_mse_fwd(const float* a, const float* b, long long n, float coef, float*
 int sisr_mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
                  float* gb, void* s) {
   return wrap(mse_bwd(a, b, n, coef, gout, ga, gb, S(s)), "mse_bwd");
+}
+
+// ------------------------------------------------------------------ image-quality metrics
+int sisr_psnr_ssim(const float* a, const float* b, int n, int c, int h, int w, float range, float* workspace,
+                   float* psnr, float* ssim, void* s) {
+  if (!a || !b || !workspace || !psnr || !ssim) return fail(1, "psnr_ssim: null argument");
+  if (h < 11 || w < 11) return fail(1, "psnr_ssim: images must be at least 11 x 11 (SSIM window)");
+  return wrap(psnr_ssim(a, b, n, c, h, w, range, workspace, psnr, ssim, S(s)), "psnr_ssim");
 }
 
 // ------------------------------------------------------------------ SyncBN over NVLink peer memory

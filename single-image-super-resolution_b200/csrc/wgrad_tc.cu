@@ -14,6 +14,7 @@
 #include "wgrad_tc.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "igemm.h"
 #include "ptx.cuh"
@@ -416,13 +417,19 @@ Plan make_plan(int n, int oh, int ow, int cin, int cout, int stride = 0, int ps 
   // waves / splits (time of the slowest SM), ties go to fewer splits (less partial-sum traffic)
   int splits = 1;
   double best = 1e30;
+  // cost of one more split, in k-blocks: its fp32 partial (Cout x 9 x Cin) is written once and read once by the
+  // finish kernel, and the CTA pays its prologue / pipeline fill.  SISR_WGRAD_SPLIT_COST overrides (A-B timing).
+  static const double split_cost = [] {
+    const char* e = getenv("SISR_WGRAD_SPLIT_COST");
+    return e ? atof(e) : 0.02;
+  }();
   const int max_splits = pl.total_kb < 148 ? pl.total_kb : 148;
   for (int sp = 1; sp <= max_splits; ++sp) {
     const int kbs = (pl.total_kb + sp - 1) / sp;
     const int real = (pl.total_kb + kbs - 1) / kbs;
     const long long waves = (static_cast<long long>(pl.tiles) * real + 147) / 148;
     // the kernel is MMA-bound (20 N=64 instructions per k-block): spread over all SMs, avoid partial waves
-    const double cost = static_cast<double>(waves) * (kbs + fixed_cost) + 0.02 * real;
+    const double cost = static_cast<double>(waves) * (kbs + fixed_cost) + split_cost * real;
     if (cost < best - 1e-9) {
       best = cost;
       splits = real;

@@ -8,6 +8,9 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from oracle import srgan_oracle as O
+from oracle import state_factory as S
+
 pytestmark = pytest.mark.gpu
 
 TOL_BF16 = 1e-2
@@ -332,3 +335,37 @@ def test_pixel_shuffle2_standalone_bit_exact(cuda, shape):
     gy = bf(torch.randn(n, c4 // 4, 2 * h, 2 * w, generator=gen))
     y.backward(nhwc(gy))
     assert torch.equal(nchw(xd.grad), F.pixel_unshuffle(gy, 2))
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 96, 96), (2, 1, 11, 17), (5, 3, 40, 23)])
+def test_psnr_ssim_vs_oracle(cuda, shape):
+    """sisr_psnr_ssim against the oracle's published-definition SSIM / PSNR (README.md:88 todo)."""
+    import sisr_b200 as m
+    g = torch.Generator().manual_seed(11)
+    a = torch.rand(shape, generator=g) * 2 - 1
+    b = (a + 0.1 * torch.randn(shape, generator=g)).clamp(-1, 1)
+    psnr, ssim = m.psnr_ssim(a.cuda(), b.cuda())
+    assert torch.allclose(psnr.cpu().double(), O.psnr_per_image(a, b), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(ssim.cpu().double(), O.ssim(a, b), rtol=1e-4, atol=1e-4)
+    p2, s2 = m.psnr_ssim(a.cuda(), a.cuda())
+    assert torch.isinf(p2).all() and torch.allclose(s2.cpu(), torch.ones(shape[0]))
+    with pytest.raises(Exception):
+        m.psnr_ssim(a[..., :8, :8].cuda(), b[..., :8, :8].cuda())
+
+
+def test_viewer_flow_eval_mode(cuda):
+    """visualisation.py:46-52 without the plotting: LR / SR = G(LR) / HR / UR = G(HR) in eval mode; the
+    generator's buffers must not move (eval: BN running statistics, no spectral-norm iteration)."""
+    import sisr_b200 as m
+    net = m.GeneratorSuffix(m.Generator(2, 64, 256, [2], use_sn=True))
+    torch.nn.Module.load_state_dict(net, S.clone_state(S.generator_state(77, n_blocks=2, n_suffix=1)), strict=True)
+    net = net.cuda().train()
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    hr = S.synthetic_hr(78, 2, 32).cuda()
+    out = m.evaluate(net, hr, (8, 8))
+    assert out["lr"].shape == (2, 3, 8, 8) and out["sr"].shape == (2, 3, 32, 32) and out["ur"].shape == (2, 3, 128, 128)
+    assert out["psnr"].shape == (2,) and out["ssim"].shape == (2,) and net.training
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    ref = O.generator_forward(S.generator_state(77, n_blocks=2, n_suffix=1), O.lr_from_hr(hr.cpu(), (8, 8)), training=False)
+    assert O.psnr(out["sr"].cpu(), ref) >= 50.0

@@ -3,6 +3,8 @@ oracle/validate_against_reference.py recorded from the real reference modules.""
 import os
 
 import pytest
+import math
+
 import torch
 
 from oracle import srgan_oracle as O
@@ -154,3 +156,20 @@ def test_adam_restatement_matches_torch():
         opt.step()
         mine.step(st, {"w": g})
     assert O.rel_l2(st["w"], p.detach()) < 1e-6
+
+
+def test_ssim_restatement_properties():
+    """The oracle's SSIM (published definition; the reference has none): 1 for identical images, symmetric,
+    lower for a noisier copy, and equal to the closed form for constant images."""
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(2, 3, 24, 24, generator=g) * 2 - 1
+    assert torch.allclose(O.ssim(a, a), torch.ones(2, dtype=torch.float64))
+    b1 = (a + 0.05 * torch.randn(a.shape, generator=g)).clamp(-1, 1)
+    b2 = (a + 0.3 * torch.randn(a.shape, generator=g)).clamp(-1, 1)
+    assert torch.allclose(O.ssim(a, b1), O.ssim(b1, a))
+    assert (O.ssim(a, b1) > O.ssim(a, b2)).all() and (O.ssim(a, b2) < 0.9).all()
+    x, y = torch.full((1, 1, 16, 16), 0.5), torch.full((1, 1, 16, 16), -0.25)
+    c1, c2 = (0.01 * 2) ** 2, (0.03 * 2) ** 2
+    want = (2 * 0.5 * -0.25 + c1) * c2 / ((0.25 + 0.0625 + c1) * c2)
+    assert abs(float(O.ssim(x, y)) - want) < 1e-9
+    assert abs(float(O.psnr_per_image(x, y)) - 10 * math.log10(4 / 0.75 ** 2)) < 1e-9

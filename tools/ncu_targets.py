@@ -1,0 +1,96 @@
+"""One launch of every kernel family of the SRGAN step at its config-2 shape, through the C ABI, for
+`ncu --set full` (measurement infrastructure).  Run plain first, then under ncu:
+
+    python tools/ncu_targets.py && ncu --set full --clock-control none --import-source on -c 80 \
+        -o gpurun_out/r2_targets python tools/ncu_targets.py
+
+Every launch is preceded by one untimed launch of the same kernel on other buffers (module load, TMA descriptor
+cache, L2 state comparable to the step: the trunk tensors are L2-resident there too); pass `--profile-second`
+semantics by skipping odd launches when reading the report (names repeat in pairs)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sisr_b200 import _lib
+
+B = int(os.environ.get("BATCH", "64"))
+dev = torch.device("cuda")
+st = torch.cuda.current_stream().cuda_stream
+
+
+def conv(h, cin, cout, stride=1, stats=False, kinds=("fprop", "dgrad", "wgrad")):
+    oh = (h + 2 - 3) // stride + 1
+    d = _lib.ConvDesc(B, h, h, cin, oh, oh, cout, 3, stride, 1, 0)
+    for rep in range(2):
+        x = torch.randn(B, h, h, cin, device=dev).to(torch.bfloat16)
+        wf = (torch.randn(cout, 3, 3, cin, device=dev) * 0.02).to(torch.bfloat16)
+        wd = (torch.randn(cin, 3, 3, cout, device=dev) * 0.02).to(torch.bfloat16)
+        y = torch.randn(B, oh, oh, cout, device=dev).to(torch.bfloat16)
+        dx = torch.empty_like(x)
+        stt = torch.empty(_lib.query("sisr_stats_rows") * 2 * cout, device=dev) if stats else None
+        bias = torch.zeros(cout, device=dev)
+        if "fprop" in kinds:
+            _lib.call("sisr_conv_fprop", d, x, wf, bias, 0, 0.0, None, y, None, stt, st)
+        if "dgrad" in kinds:
+            _lib.call("sisr_conv_dgrad", d, y, wf, wd, dx, st)
+        if "wgrad" in kinds:
+            w = torch.randn(cout, cin, 3, 3, device=dev) * 0.02
+            u = torch.nn.functional.normalize(torch.randn(cout, device=dev), dim=0)
+            v = torch.nn.functional.normalize(torch.randn(cin * 9, device=dev), dim=0)
+            sig = torch.ones(1, device=dev)
+            dw, db = torch.empty_like(w), torch.empty(cout, device=dev)
+            ws = torch.empty(_lib.query("sisr_conv_wgrad_fused_workspace_bytes", d), dtype=torch.uint8, device=dev)
+            _lib.call("sisr_conv_wgrad_fused", d, x, y, w, u, v, sig, dw, None, db, 0, ws, st)
+        torch.cuda.synchronize()
+
+
+def elementwise(rows, c):
+    for rep in range(2):
+        y = torch.randn(rows, c, device=dev).to(torch.bfloat16)
+        g = torch.randn(rows, c, device=dev).to(torch.bfloat16)
+        out = torch.empty_like(y)
+        scale, shift = torch.rand(c, device=dev) + 0.5, torch.randn(c, device=dev)
+        mean, invstd = torch.randn(c, device=dev) * 0.1, torch.rand(c, device=dev) + 0.5
+        slope = torch.full((1,), 0.25, device=dev)
+        sums, colsum = torch.zeros(2 * c + 1, device=dev), torch.zeros(c, device=dev)
+        _lib.call("sisr_bn_apply", y, scale, shift, 3, 0.0, slope, None, out, rows, c, st)
+        _lib.call("sisr_bn_bwd_reduce", g, y, mean, invstd, scale, shift, 3, 0.0, slope, sums, rows, c, st)
+        _lib.call("sisr_bn_bwd_apply", g, y, mean, invstd, scale, shift, 3, 0.0, slope, sums, float(rows), out,
+                  colsum, rows, c, st)
+        torch.cuda.synchronize()
+
+
+def dhead():
+    n, fc_in, fc_mid = B, 18432, 1024
+    for rep in range(2):
+        xf = torch.randn(n, fc_in, device=dev).to(torch.bfloat16)
+        w0, b0 = torch.randn(fc_mid, fc_in, device=dev) * 0.01, torch.zeros(fc_mid, device=dev)
+        w2, b2 = torch.randn(1, fc_mid, device=dev) * 0.03, torch.zeros(1, device=dev)
+        hbuf, p = torch.empty(n, fc_mid, device=dev), torch.empty(n, 1, device=dev)
+        _lib.call("sisr_dhead_forward", xf, w0, b0, w2, b2, 0.01, hbuf, p, n, fc_in, fc_mid, st)
+        dh, dw0 = torch.empty(n, fc_mid, device=dev), torch.empty_like(w0)
+        db0, dw2, db2 = torch.empty(fc_mid, device=dev), torch.empty(1, fc_mid, device=dev), torch.empty(1, device=dev)
+        dxf = torch.empty(n, fc_in, device=dev)
+        gp = torch.full((n, 1), 1.0 / n, device=dev)
+        _lib.call("sisr_dhead_backward", xf, w0, w2, hbuf, p, gp, 0.01, dh, dw0, db0, dw2, db2, dxf, n, fc_in, fc_mid,
+                  1, st)
+        torch.cuda.synchronize()
+
+
+def main():
+    conv(24, 64, 64, stats=True)                       # generator trunk: igemm_th, wgrad_tc + reduce_finish_small
+    conv(96, 64, 64, kinds=("fprop", "dgrad"))         # VGG conv1_2
+    conv(48, 128, 128, kinds=("fprop", "dgrad"))       # VGG conv2_2: igemm_t_kernel
+    conv(24, 256, 256)                                 # VGG conv3_x / D: igemm_tc_kernel<256,4>, wide wgrad
+    conv(12, 512, 512, kinds=("fprop", "dgrad"))       # VGG conv4_x
+    conv(48, 128, 128, stride=2, stats=True)           # D stride 2: igemm_tc_kernel<128,6> dgrad classes
+    conv(12, 256, 512, stats=True, kinds=("wgrad",))   # D: wgrad + cooperative reduce_finish
+    elementwise(B * 24 * 24, 64)                       # trunk BN kernels (L2-resident 4.7 MB tensors)
+    elementwise(B * 96 * 96, 64)                       # 75 MB tensors: HBM-bound
+    dhead()                                            # wstream_gemm / dhead_wgrad
+    print("ncu_targets: done")
+
+
+if __name__ == "__main__":
+    main()
