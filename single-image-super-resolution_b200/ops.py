@@ -91,6 +91,13 @@ def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise _lib.SisrError(f"{what}: tensor is on {t.device}; the sisr_b200 operators run only on "
                              "CUDA (sm_100a) - there is no CPU path")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's stream; nn.DataParallel replicas (config.py:114-118) run in
+        # threads on other devices and would also share this module's per-step state - use one process per
+        # GPU (parallel.init_distributed / GradSync) instead
+        raise _lib.SisrError(f"{what}: tensor is on {t.device} but the current device is cuda:"
+                             f"{torch.cuda.current_device()}; single-process multi-device execution "
+                             "(nn.DataParallel) is not supported - run one process per GPU")
 
 
 _dist_group = None
@@ -402,6 +409,8 @@ class ConvCfg:
     want_stats: bool = False   # BN batch statistics from the conv epilogue
     training: bool = True      # spectral-norm power iteration on/off
     out_nchw_f32: bool = False  # edge layer: write fp32 NCHW (+tanh) for the module boundary
+    sync_wgrad: bool = False   # weight gradient returned through autograd even in side-stream mode (the weight
+                               # is a derived tensor, e.g. zero-padded, whose gradient must flow on)
 
 
 def _desc(x_shape, cout, k, cfg: ConvCfg) -> ConvDesc:
@@ -457,14 +466,17 @@ class Conv2dFn(torch.autograd.Function):
             call("sisr_conv_fprop", d, x, wf, bias_used, cfg.act, cfg.leaky_slope, slope, y, None, stats, st)
         ctx.cfg, ctx.d = cfg, d
         ctx.weight_ref, ctx.bias_ref = weight, bias
-        src = _relu_outputs.get(x.data_ptr())
+        src = _relu_outputs.pop(x.data_ptr(), None)      # consumed by the one conv that reads this tensor
         ctx.input_is_relu = bool(src is not None and src.shape == x.shape and need_dx and not cfg.out_nchw_f32
                                  and not _NO_MASK_FUSION
                                  and query("sisr_conv_dgrad_fuses_mask", d))
         if (cfg.act == ACT_RELU and need_dx and not cfg.out_nchw_f32 and cfg.ps_r != 2 and
                 (_skip_param_grads or not (weight.requires_grad or bias.requires_grad))):
-            if len(_relu_outputs) > 256:      # callers that never reach begin_step()
-                _relu_outputs.clear()
+            # entries are removed when consumed; the ones never consumed (a ReLU output that feeds a max-pool)
+            # are evicted oldest-first, so that callers that never reach begin_step() (the drop-in mode of
+            # INTEGRATION.md) pin at most 16 activations instead of growing by four per VGG forward
+            while len(_relu_outputs) >= 16:
+                del _relu_outputs[next(iter(_relu_outputs))]
             _relu_outputs[y.data_ptr()] = y
         if _async["track"] and not _skip_param_grads and (weight.requires_grad or bias.requires_grad):
             k_ = weight.data_ptr()
@@ -519,8 +531,8 @@ class Conv2dFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             if ctx.input_is_relu:
                 call("sisr_conv_dgrad_masked", d, dpre, wf, wd, dx, x, 0.0, st)
-                if len(_premasked) > 256:     # callers that never reach begin_step()
-                    _premasked.clear()
+                while len(_premasked) >= 16:  # callers that never reach begin_step(): oldest first
+                    del _premasked[next(iter(_premasked))]
                 _premasked[dx.data_ptr()] = dx
             else:
                 call("sisr_conv_dgrad", d, dpre, wf, wd, dx, st)
@@ -529,7 +541,7 @@ class Conv2dFn(torch.autograd.Function):
             nbytes = query("sisr_conv_wgrad_fused_workspace_bytes", d)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             sig = sigma if ctx.has_sn else None
-            if _async["on"]:
+            if _async["on"] and not cfg.sync_wgrad:
                 key = weight.data_ptr()
                 prev = _async["pending"].get(key)
                 if prev is None:
@@ -653,8 +665,8 @@ class BnActFn(torch.autograd.Function):
                  slope, red, ctx.count, dy, colsum, rows, c, st)
             if colsum is not None:
                 # per-channel sum of dy = bias gradient of the producing conv; handed to its backward
-                if len(_colsum_cache) > 256:
-                    _colsum_cache.clear()
+                while len(_colsum_cache) >= 16:
+                    del _colsum_cache[next(iter(_colsum_cache))]
                 _colsum_cache[dy.data_ptr()] = (dy, colsum)
         dgamma = dbeta = dslope = None
         if not ctx.skip_params:

@@ -143,8 +143,29 @@ def test_progressive_generator_vs_reference_golden(cuda, golden_dir, n_suffix):
     with torch.no_grad():
         ye = net(g["x"].cuda())
     assert rel(ye, g["y_eval"]) < 1e-2
-    with pytest.raises(NotImplementedError):
-        mp.GeneratorSuffix(net.beginning, 4)
+    if n_suffix == 2:
+        # the reference's own smoke test chains one more stage down to 4 channels
+        # (model_generator_progressive.py:67-86: g3 = GeneratorSuffix(g2.beginning, n_features=4))
+        st3 = S.progressive_state(g["seed"], n_blocks=2, nf=64, n_suffix=3)
+        net.train()
+        g3 = mp.GeneratorSuffix(net.beginning, 4).cuda().train()
+        assert set(g3.state_dict()) == set(st3)
+        torch.nn.Module.load_state_dict(g3, S.clone_state(st3), strict=True)
+        y3 = g3(g["x"].cuda())
+        assert y3.shape == (g["x"].shape[0], 3, 8 * 8, 8 * 8)
+        names = O.trainable_names(st3)
+        leaf = O._leaf(S.clone_state(st3), names)
+        y3_ref = O.progressive_forward(leaf, g["x"], training=True)
+        assert rel(y3, y3_ref) < 1e-2, rel(y3, y3_ref)
+        gy3 = torch.randn(y3_ref.shape, generator=torch.Generator().manual_seed(9))
+        want = dict(zip(names, torch.autograd.grad((y3_ref * gy3).sum(), [leaf[k] for k in names])))
+        (y3 * gy3.cuda()).sum().backward()
+        got = {k: p.grad for k, p in g3.named_parameters()}
+        for k in ("end.0.weight", "end.0.bias", "beginning.1.weight", "beginning.3.weight"):
+            assert got[k] is not None and got[k].shape == want[k].shape, k
+            assert cos(got[k], want[k]) > 0.9, (k, cos(got[k], want[k]))
+        with pytest.raises(NotImplementedError):
+            mp.GeneratorSuffix(net.beginning, 12)
 
 
 def test_discriminator_vs_reference_golden(cuda, golden_dir):
