@@ -212,6 +212,28 @@ def test_batchnorm_act(cuda, act, residual, training):
         assert rel(sd.grad, slope.grad) < TOL_BF16
 
 
+@pytest.mark.parametrize("mean_over_sigma", [8.0, 64.0])
+def test_batchnorm_large_mean_channels(cuda, mean_over_sigma):
+    """Train-mode statistics as E[x^2] - E[x]^2 in fp32 (csrc/elementwise.cu bn_finalize, csrc/peer.cu) on
+    channels whose mean is far from zero: the cancellation costs (mean/sigma)^2 x 6e-8 relative on the variance
+    - 2.5e-4 at mean/sigma = 64, far inside the bf16 tolerance.  (The activations of this network are
+    zero-centred by the preceding BN / PReLU; |mean| >> 100 sigma would need a shifted accumulation.)"""
+    from sisr_b200 import ops
+    c = 64
+    g = torch.Generator().manual_seed(5)
+    # values on a bf16-exact grid around a large mean, so that the input is the same on both sides
+    y = bf(mean_over_sigma + torch.randn(4, c, 12, 12, generator=g))
+    bn = torch.nn.BatchNorm2d(c).train()
+    o = bn(y)
+    yd = nhwc(y)
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    out = ops.BnActFn.apply(yd, None, bn.weight.detach().cuda(), bn.bias.detach().cuda(), rm, rv, nbt, None, None,
+                            ops.BnCfg(act=ops.ACT_NONE, training=True))
+    assert rel(nchw(out), o) < TOL_BF16
+    assert rel(rv, bn.running_var) < 2e-3 and rel(rm, bn.running_mean) < 1e-5
+
+
 def test_maxpool(cuda):
     from sisr_b200 import ops
     g = torch.Generator().manual_seed(2)
