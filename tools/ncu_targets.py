@@ -15,6 +15,7 @@ import torch
 from sisr_b200 import _lib
 
 B = int(os.environ.get("BATCH", "64"))
+REPS = 1 if os.environ.get("NCU_SINGLE") else 2      # NCU_SINGLE=1: one launch per kernel (halves the ncu time)
 dev = torch.device("cuda")
 st = torch.cuda.current_stream().cuda_stream
 
@@ -22,7 +23,7 @@ st = torch.cuda.current_stream().cuda_stream
 def conv(h, cin, cout, stride=1, stats=False, kinds=("fprop", "dgrad", "wgrad")):
     oh = (h + 2 - 3) // stride + 1
     d = _lib.ConvDesc(B, h, h, cin, oh, oh, cout, 3, stride, 1, 0)
-    for rep in range(2):
+    for rep in range(REPS):
         x = torch.randn(B, h, h, cin, device=dev).to(torch.bfloat16)
         wf = (torch.randn(cout, 3, 3, cin, device=dev) * 0.02).to(torch.bfloat16)
         wd = (torch.randn(cin, 3, 3, cout, device=dev) * 0.02).to(torch.bfloat16)
@@ -46,7 +47,7 @@ def conv(h, cin, cout, stride=1, stats=False, kinds=("fprop", "dgrad", "wgrad"))
 
 
 def elementwise(rows, c):
-    for rep in range(2):
+    for rep in range(REPS):
         y = torch.randn(rows, c, device=dev).to(torch.bfloat16)
         g = torch.randn(rows, c, device=dev).to(torch.bfloat16)
         out = torch.empty_like(y)
@@ -63,7 +64,7 @@ def elementwise(rows, c):
 
 def dhead():
     n, fc_in, fc_mid = B, 18432, 1024
-    for rep in range(2):
+    for rep in range(REPS):
         xf = torch.randn(n, fc_in, device=dev).to(torch.bfloat16)
         w0, b0 = torch.randn(fc_mid, fc_in, device=dev) * 0.01, torch.zeros(fc_mid, device=dev)
         w2, b2 = torch.randn(1, fc_mid, device=dev) * 0.03, torch.zeros(1, device=dev)
