@@ -126,6 +126,11 @@ igemm_th_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         tma_load_2d(smem_u32(smem_w + g * kWTile), &tmap_w, wb, p.k_lo[g], 0);
         if (p.k_hi[g] >= 0) tma_load_2d(smem_u32(smem_w + g * kWTile + kWTile / 2), &tmap_w, wb, p.k_hi[g], 0);
       }
+      // Programmatic dependent launch: everything above (barriers, TMEM, zero fill, the 72 KB of weights -
+      // prepared long before the preceding kernel) overlaps the tail of the kernel that produces the input
+      // tensor; the activation boxes wait for its completion.  Every global write of this kernel happens
+      // after an MMA that consumed such a box, i.e. after this wait.  (No-op for an ordinary launch.)
+      pdl_wait();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t bb = it % p.nbox, use = it / p.nbox;
@@ -323,8 +328,9 @@ bool make_plan(const IgemmProblem& p, THPlan& best) {
     const long long tiles = imgs * tiles_h;
     const long long waves = (tiles + sms() - 1) / sms();
     const int fixed = kGroups * kWTile + kXBytes + kStageBytes + 1024;
-    int nbox = waves > 1 ? 2 : 1;
-    if (fixed + nbox * box_alloc > 225 * 1024) nbox = 1;
+    // several tiles per CTA need two box buffers (the load of tile i+1 under the MMAs of tile i): with one
+    // buffer VGG conv1_2 (96 x 96, 21 tiles per CTA) measured 130 us against 120 us on the im2col-fed kernel
+    const int nbox = waves > 1 ? 2 : 1;
     if (fixed + nbox * box_alloc > 225 * 1024) continue;
     const double mma = 4.0 * kGroups * chunks * (chunk_n * 0.5 + 38.0 > 94.0 ? chunk_n * 0.5 + 38.0 : 94.0);
     const double epi = 14.0 * n_total;                 // TMEM reads, hand-over, transpose, stores
@@ -403,7 +409,22 @@ int igemm_th_launch(const IgemmProblem& p, cudaStream_t stream) {
     configured = pl.smem;
   }
   const int grid = tp.num_tiles < sms() ? tp.num_tiles : sms();
-  igemm_th_kernel<<<grid, kThreads, pl.smem, stream>>>(tx, tw, tp);
+  static const int pdl = [] { const char* e = getenv("SISR_TH_PDL"); return e && e[0] == '0' ? 0 : 1; }();
+  if (pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, igemm_th_kernel, tx, tw, tp);
+  } else {
+    igemm_th_kernel<<<grid, kThreads, pl.smem, stream>>>(tx, tw, tp);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "igemm_th launch: %s", cudaGetErrorString(e));
