@@ -332,6 +332,7 @@ bool make_plan(const IgemmProblem& p, THPlan& best) {
     // buffer VGG conv1_2 (96 x 96, 21 tiles per CTA) measured 130 us against 120 us on the im2col-fed kernel
     const int nbox = waves > 1 ? 2 : 1;
     if (fixed + nbox * box_alloc > 225 * 1024) continue;
+    if (waves > 1 && n_total < 192) continue;          // short instructions sit on the 94-cycle floor
     const double mma = 4.0 * kGroups * chunks * (chunk_n * 0.5 + 38.0 > 94.0 ? chunk_n * 0.5 + 38.0 : 94.0);
     const double epi = 14.0 * n_total;                 // TMEM reads, hand-over, transpose, stores
     const double c = static_cast<double>(waves) * (mma + epi + 1500.0) * (1.0 + 0.02 * (tiles_h * R - p.H));
