@@ -40,6 +40,7 @@ struct WParams {
   int ci_blocks, co_blocks, splits, kb_per_split, total_kb;
   int Cin, Cout;
   int ps;                // dY stored pixel-shuffled
+  int atomic;            // 1: every split adds into ONE zeroed [Cout][9][Cin] buffer (red.global.add.f32)
   float* out;            // [splits][Cout][9][Cin] (splits > 1) or final [Cout][9][Cin]
 };
 
@@ -144,7 +145,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const int ci = cib * 64 + (row & 63);
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
-    float* outp = p.out + static_cast<size_t>(split) * p.Cout * 9 * p.Cin;
+    float* outp = p.out + (p.atomic ? 0 : static_cast<size_t>(split) * p.Cout * 9 * p.Cin);
 #pragma unroll 1
     for (int q = 0; q < kPairs; ++q) {
       const int tap = 2 * q + (row >> 6);
@@ -154,10 +155,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + q * 64 + c * 32, raw);
         tmem_ld_wait();
         if (tap < 9) {
+          if (p.atomic) {
+            // small layers (the 64 x 576 trunk gradient): the pixel splits add straight into one L2-resident
+            // buffer (a warp's 32 lanes = 32 consecutive ci = one 128-byte reduction) instead of writing
+            // `splits` partial copies that a second kernel reads back
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int co = cob * 64 + c * 32 + i;
-            outp[(static_cast<size_t>(co) * 9 + tap) * p.Cin + ci] = __uint_as_float(raw[i]);
+            for (int i = 0; i < 32; ++i) {
+              const int co = cob * 64 + c * 32 + i;
+              atomicAdd(&outp[(static_cast<size_t>(co) * 9 + tap) * p.Cin + ci], __uint_as_float(raw[i]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int co = cob * 64 + c * 32 + i;
+              outp[(static_cast<size_t>(co) * 9 + tap) * p.Cin + ci] = __uint_as_float(raw[i]);
+            }
           }
         }
       }
@@ -379,8 +391,11 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long long
   for (int i = threadIdx.x; i < classes * C; i += blockDim.x) atomicAdd(&dbias[i], s_acc[i]);
 }
 
+constexpr long long kAtomicMaxFloats = 1 << 18;      // gradients up to 1 MB accumulate with L2 reductions
+int g_wgrad_atomic = [] { const char* e = getenv("SISR_WGRAD_ATOMIC"); return e && e[0] == '0' ? 0 : 1; }();
+
 struct Plan {
-  int total_kb, splits, kb_per_split, tiles;
+  int total_kb, splits, kb_per_split, tiles, atomic;
   // halo variant (halo = 1): a "k-block" is one unit of R image rows
   int halo, R, PW, k_steps, x_alloc, stage_bytes, stages, units_per_img;
 };
@@ -423,13 +438,15 @@ Plan make_plan(int n, int oh, int ow, int cin, int cout, int stride = 0, int ps 
     const char* e = getenv("SISR_WGRAD_SPLIT_COST");
     return e ? atof(e) : 0.1;      // 0.02 -> 0.1: step 8.38 -> 8.21 ms (r2 sweep 0.02 / 0.1 / 0.2 / 0.4)
   }();
+  pl.atomic = (g_wgrad_atomic && !pl.halo && static_cast<long long>(cout) * 9 * cin <= kAtomicMaxFloats) ? 1 : 0;
+  const double per_split = pl.atomic ? 0.03 : split_cost;     // no partial copy to write and read back
   const int max_splits = pl.total_kb < 148 ? pl.total_kb : 148;
   for (int sp = 1; sp <= max_splits; ++sp) {
     const int kbs = (pl.total_kb + sp - 1) / sp;
     const int real = (pl.total_kb + kbs - 1) / kbs;
     const long long waves = (static_cast<long long>(pl.tiles) * real + 147) / 148;
     // the kernel is MMA-bound (20 N=64 instructions per k-block): spread over all SMs, avoid partial waves
-    const double cost = static_cast<double>(waves) * (kbs + fixed_cost) + split_cost * real;
+    const double cost = static_cast<double>(waves) * (kbs + fixed_cost) + per_split * real;
     if (cost < best - 1e-9) {
       best = cost;
       splits = real;
@@ -437,6 +454,7 @@ Plan make_plan(int n, int oh, int ow, int cin, int cout, int stride = 0, int ps 
   }
   pl.kb_per_split = (pl.total_kb + splits - 1) / splits;
   pl.splits = (pl.total_kb + pl.kb_per_split - 1) / pl.kb_per_split;
+  if (pl.splits <= 1) pl.atomic = 0;
   return pl;
 }
 
@@ -463,13 +481,15 @@ size_t wgrad_tc_workspace_bytes(int n, int h, int w, int cin, int oh, int ow, in
 int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, float* dbias,
                     void* workspace, int n, int h, int w, int cin, int oh, int ow, int cout, int stride,
                     int ps_r, cudaStream_t s, int* splits_out) {
-  const Plan pl = make_plan(n, oh, ow, cin, cout, stride, ps_r == 2);
+  Plan pl = make_plan(n, oh, ow, cin, cout, stride, ps_r == 2);
   const bool keep_partials = g == nullptr;   // caller reduces (weight_grad_reduce_finish)
   if ((pl.splits > 1 || keep_partials) && !workspace) {
     snprintf(g_err, sizeof g_err, "wgrad: split-K workspace missing");
     return 1;
   }
-  if (splits_out) *splits_out = pl.splits;
+  if (pl.atomic)     // the splits add into the first [Cout][9][Cin] slot of the workspace
+    cudaMemsetAsync(workspace, 0, sizeof(float) * static_cast<size_t>(cout) * 9 * cin, s);
+  if (splits_out) *splits_out = pl.atomic ? 1 : pl.splits;
   CUtensorMap tx, tdy;
   if (pl.halo) {
     if (make_tmap_tiled_nhwc_bf16(&tx, x, n, h, w, cin, 64, pl.PW, pl.R + 2) ||
@@ -524,6 +544,7 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
   p.ci_blocks = cin / 64; p.co_blocks = cout / 64;
   p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.total_kb = pl.total_kb;
   p.Cin = cin; p.Cout = cout; p.ps = ps;
+  p.atomic = pl.atomic;
   p.out = (pl.splits > 1 || keep_partials) ? static_cast<float*>(workspace) : g;
   const int smem_bytes = kStages * kStageBytes + 1024;
   static bool configured = false;
@@ -543,7 +564,7 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
   if (pl.splits > 1 && !keep_partials) {
     const long long total4 = static_cast<long long>(cout) * 9 * cin / 4;
     splitk_reduce_kernel<<<static_cast<int>((total4 + 15) / 16), 256, 0, s>>>(
-        static_cast<const float*>(workspace), g, total4, pl.splits);
+        static_cast<const float*>(workspace), g, total4, pl.atomic ? 1 : pl.splits);
   }
   if (dbias) {
     cudaMemsetAsync(dbias, 0, sizeof(float) * cout, s);
