@@ -502,11 +502,7 @@ def run_ours(args):
     HR, LRS = cfg["hr"], cfg["lr"]
     use_graph = not args.no_graph      # NCCL all-reduces and the peer-memory SyncBN kernels are captured too
     bucket = int(os.environ.get("SISR_BUCKET_MB", "0")) << 20
-    gs = (parallel.GradSync(bucket_bytes=bucket) if bucket else parallel.GradSync()) \
-        if (world > 1 and not os.environ.get("SISR_DIAG_NO_GRADSYNC")) else None
-    if os.environ.get("SISR_DIAG_NO_SYNCBN"):      # attribution experiments only (results differ from the spec)
-        from sisr_b200 import ops as _ops
-        _ops.set_sync_group(None)
+    gs = (parallel.GradSync(bucket_bytes=bucket) if bucket else parallel.GradSync()) if world > 1 else None
     tr = build_trainer(dev, batch, world, gs, args.config)
     gen = torch.Generator().manual_seed(1234 + rank)          # synthetic HR patches ~ U[-1, 1]
     hr_host = (torch.rand((batch, 3, HR, HR), generator=gen) * 2 - 1).pin_memory()

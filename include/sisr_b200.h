@@ -42,17 +42,9 @@ const char* sisr_last_error(void);
 int sisr_abi_version(void);
 /* number of partial-sum rows of a `stats` buffer (= SM count: one row per persistent CTA) */
 int sisr_stats_rows(void);
-/* debug / A-B timing: conv engine A-operand feed: 0 = im2col-mode TMA only, 1 = cost model (default),
- * 2 = halo tiles whenever the geometry allows */
-int sisr_debug_halo_mode(int mode);
 /* debug / A-B timing: 0 = layers with cout <= 128 use the 128-pixel x cout tiles instead of the
  * 128-channel x 256-pixel (transposed) tiles */
 int sisr_debug_transposed(int on);
-/* 1: convs with Cout % 256 == 0 run on the CTA-pair (tcgen05 cta_group::2, M = 256) kernel.  Round-2 draft:
- * compiled, not yet validated on hardware; default 0. */
-int sisr_debug_pair_mode(int on);
-/* debug / A-B timing: 0 = weight gradients always use the im2col-fed kernel (never the halo boxes) */
-int sisr_debug_wgrad_halo(int on);
 /* debug / A-B timing: 0 = the 64 -> 64 channel stride-1 layers (generator trunk, model_generator.py:10,13,39)
  * do not use the transposed halo-fed kernel with stacked filter taps (csrc/igemm_th.cu); default 1 */
 int sisr_debug_th_mode(int on);

@@ -68,10 +68,7 @@ extern "C" {
 const char* sisr_last_error(void) { return g_err; }
 int sisr_abi_version(void) { return 2; }
 int sisr_stats_rows(void) { return igemm_max_ctas(); }
-int sisr_debug_halo_mode(int mode) { igemm_set_halo_mode(mode); return 0; }
 int sisr_debug_transposed(int on) { igemm_set_transposed(on); return 0; }
-int sisr_debug_pair_mode(int on) { igemm_set_pair(on); return 0; }
-int sisr_debug_wgrad_halo(int on) { wgrad_tc_set_halo(on); return 0; }
 int sisr_debug_th_mode(int on) { igemm_set_th(on); return 0; }
 int sisr_conv_uses_tensor_cores(const sisr_conv_desc* d) { return desc_ok(d) && tc_shape(d) ? 1 : 0; }
 

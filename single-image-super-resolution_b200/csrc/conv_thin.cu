@@ -859,11 +859,9 @@ FastDiv make_fastdiv(uint32_t d) {
   const unsigned long long one = 1ull << (31 + l);
   return FastDiv{static_cast<uint32_t>((one + d - 1) / d), 31 + l, d};
 }
-// first-generation kernels on request (A/B): SISR_THIN_V1=1
-bool thin_v1() {
-  static const bool v = [] { const char* e = getenv("SISR_THIN_V1"); return e && e[0] == '1'; }();
-  return v;
-}
+// (the first-generation thin_*_mma kernels below still serve the 9x9 layer; their use for the 3x3 layers
+// was an A-B switch in round 1 and is gone)
+constexpr bool thin_v1() { return false; }
 // rows per block of thin_out3: the fp32 tap-product band (R+2) x W x 29 words must fit; two blocks per SM
 // when that leaves at least 4 rows, else one
 int thin_out3_rows(const ThinConv& c) {

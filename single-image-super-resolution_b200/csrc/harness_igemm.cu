@@ -322,7 +322,6 @@ int main(int argc, char** argv) {
   };
   if (argc > 1 && argv[1][0] == 't') {
     // transposed halo-fed kernel with stacked taps (igemm_th.cu), 64 -> 64 channels: "harness_igemm th"
-    igemm_set_halo_mode(0);
     igemm_set_transposed(1);
     igemm_set_th(1);
     printf("-- transposed halo kernel, stacked taps (64 -> 64)\n");
@@ -355,49 +354,13 @@ int main(int argc, char** argv) {
     return fails ? 1 : 0;
   }
   igemm_set_th(0);
-  igemm_set_halo_mode(0);
   igemm_set_transposed(1);
   printf("-- default engine (transposed tiles for Cout <= 128)\n");
   for (const auto& cc : convs) fails += run_conv(cc, false);
   igemm_set_transposed(0);
   printf("-- im2col-fed kernel\n");
   for (const auto& cc : convs) fails += run_conv(cc, false);
-  igemm_set_halo_mode(2);
-  printf("-- halo-fed kernel wherever the geometry allows\n");
-  const ConvCase halo_extra[] = {
-      {"h_c64_48x48_n2", 2, 48, 48, 64, 64, 1, 0, ACT_NONE, 1},
-      {"h_c64_128_32x32_n2", 2, 32, 32, 64, 128, 1, 0, ACT_LEAKY, 1},
-      {"h_c128_256_24x24_n3", 3, 24, 24, 128, 256, 1, 0, ACT_RELU, 0},
-      {"h_c64_9x7_n2", 2, 9, 7, 64, 64, 1, 0, ACT_NONE, 1},
-      {"h_c256_256_96x96_n1", 1, 96, 96, 256, 256, 1, 0, ACT_RELU, 0},
-  };
-  for (const auto& cc : convs) fails += run_conv(cc, false);
-  for (const auto& cc : halo_extra) fails += run_conv(cc, false);
-  igemm_set_halo_mode(0);
-  if (argc > 1 && argv[1][0] == 'p') {
-    // CTA-pair (cta_group::2) kernel, round-2 draft: run ONLY on request ("harness_igemm pair"), wrapped in a
-    // timeout by the caller - a pipeline bug traps through the bounded mbarrier wait
-    igemm_set_pair(1);
-    printf("-- CTA-pair kernel (Cout %% 256 == 0)\n");
-    const ConvCase pair_cases[] = {
-        {"p_c256_512_6x6_n8", 8, 6, 6, 256, 512, 1, 0, ACT_RELU, 0},
-        {"p_c128_256_s2_12x12_n8", 8, 12, 12, 128, 256, 2, 0, ACT_NONE, 1},
-        {"p_c64_256_ps_24x24_n2", 2, 24, 24, 64, 256, 1, 1, ACT_PRELU, 0},
-        {"p_c128_256_24x24_n3_tail", 3, 24, 24, 128, 256, 1, 0, ACT_RELU, 1},
-        {"p_c256_256_9x7_n5_odd", 5, 9, 7, 256, 256, 1, 0, ACT_LEAKY, 1},
-    };
-    for (const auto& cc : pair_cases) fails += run_conv(cc, false);
-    const ConvCase pair_big[] = {
-        {"p_vgg_c256_24x24_n64", 64, 24, 24, 256, 256, 1, 0, ACT_RELU, 0},
-        {"p_vgg_c512_12x12_n64", 64, 12, 12, 512, 512, 1, 0, ACT_RELU, 0},
-    };
-    for (const auto& cc : pair_big) fails += run_conv(cc, true);
-    igemm_set_pair(0);
-    for (const auto& cc : pair_big) fails += run_conv(cc, true);      // same shapes on the 1-CTA kernel
-    printf("harness: %d failure(s)\n", fails);
-    return fails ? 1 : 0;
-  }
-  igemm_set_halo_mode(1);
+  igemm_set_transposed(1);
   if (argc > 1) {
     const ConvCase big[] = {
         {"trunk_c64_24x24_n64", 64, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},

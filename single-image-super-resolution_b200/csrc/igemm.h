@@ -62,9 +62,6 @@ struct IgemmProblem {
 // Returns 0 on success; message via igemm_last_error().
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream);
 bool igemm_supported(const IgemmProblem& p);
-void igemm_set_halo_mode(int mode);   // 0: im2col kernel only, 1: cost model (default), 2: halo kernel
-                                       // whenever the geometry allows (tests / A-B timing)
-void igemm_set_pair(int on);           // 1: CTA-pair (cta_group::2) kernel for Cout % 256 == 0 (round-2 draft, default 0)
 void igemm_set_transposed(int on);     // 0: never put the pixels on the UMMA N side (A-B timing)
 // Transposed halo-fed kernel with tap-pair stacking (igemm_th.cu): same-size stride-1 3x3, 64 -> 64 channels.
 // igemm_launch() routes to it first when igemm_th_supported(p).

@@ -9,18 +9,12 @@
 // main loop of tile i+1 and barrier / TMEM set-up is paid once per SM instead of once per tile.
 // B tile : BN rows x 64 k bf16, 128 B rows, hardware 128 B swizzle (K-major).
 //
-// Two ways of feeding the A (activation) operand:
-//   * igemm_tc_kernel   - im2col-mode TMA: one 128 pixel x 64 channel tile per (tap, channel block).
-//     Handles every geometry (stride 2, dgrad through PixelShuffle, parity-split dgrad) but moves
-//     9 x 16 KB of activations per 64 channels of K, which makes the thin layers L2-bandwidth bound.
-//   * igemm_halo_kernel - stride-1 same-size 3x3 convs: an M tile is R rows x TW columns of one
-//     image; ONE tiled-mode TMA box {64 ch, TW+2, R+2} (zero fill outside the image = padding)
-//     brings the tile with its halo, and the nine taps are nine UMMA descriptors into that box:
-//     accumulator row i = r*(TW+2)+c reads box row i + dy*(TW+2) + dx (a plain start-address shift,
-//     the 128 B swizzle is a function of the absolute shared-memory address - csrc/probe_shift.cu).
-//     The two halo columns of every row produce rows that are discarded (<= 10 % of the MMA work) and
-//     the activation traffic drops 9x.  When the whole weight matrix is 9 B tiles (Cin = 64, one N
-//     tile) it is loaded once per CTA and stays resident.
+// The A (activation) operand comes from im2col-mode TMA: one 128 pixel x 64 channel tile per (tap, channel
+// block).  That handles every geometry (stride 2, dgrad through PixelShuffle, parity-split dgrad).  The 64 -> 64
+// channel stride-1 layers take the halo-fed kernel of igemm_th.cu instead (one TMA box per tile, stacked taps).
+// Measured and removed (notes: profiles/r1_notes.md, profiles/r2_notes.md): a halo-box feed for these
+// 128-pixel tiles (no gain: the thin layers sat on the per-instruction floor) and a CTA-pair kernel
+// (cta_group::2, M = 256: validated, 4-10 % slower than this kernel on the 256 / 512-channel layers).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -36,7 +30,6 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kThreads = 192;
 constexpr int kATileBytes = kBM * kBK * 2;
-constexpr int kHaloABytes = 32768;   // one halo box buffer (two of them: double buffered)
 constexpr int kMaxCout = 512;        // per-CTA bias / BN statistics arrays
 
 struct EpiParams {
@@ -62,17 +55,6 @@ struct KParams {
   int cin_blocks, num_taps, n_tiles, m_tiles;
   ClassTable cls;
   IgemmTaps taps;
-  EpiParams e;
-};
-
-struct HParams {
-  int H, W;                 // image = output size
-  int TW, R, PW;            // tile columns / rows, box pitch PW = TW + 2
-  int tiles_w, tiles_hw, m_tiles, n_tiles;
-  int cin_blocks, a_bytes;
-  int resident;             // weights stay in shared memory (cin_blocks == 1, n_tiles == 1)
-  int shift[9];             // box row shift of each tap
-  int k_off[9];             // first weight column of each tap
   EpiParams e;
 };
 
@@ -381,173 +363,6 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------ CTA-pair kernel (Cout % 256 == 0)
-// ROUND-2 DRAFT: compiles for sm_100a, NOT yet run on hardware; reachable only through
-// igemm_set_pair(1) / SISR_PAIR=1 (default off) and the harness.
-// Same im2col-fed pipeline as igemm_tc_kernel<256, .>, but one tile = 256 pixels x 256 channels computed by
-// a CTA pair with tcgen05.mma.cta_group::2 (M = 256): CTA r of the pair loads the im2col rows of pixels
-// [m0 + 128 r, +128) and rows [n0 + 128 r, +128) of the weight tile, i.e. 32 KB per k-block instead of
-// 48 KB, and the per-SM shared-memory operand read per K = 16 step drops from 128 + 256 rows to 128 + 128
-// (the SS-form instruction time follows those rows, profiles/r1_notes.md).
-//   full_bar   : leader only, count 1 (leader's arrive.expect_tx of BOTH CTAs' bytes; both CTAs' TMA
-//                complete_tx on it through the peer-bit-cleared address)
-//   empty_bar, tmem_full_bar : one per CTA, signalled by the leader's multicast tcgen05.commit
-//   tmem_empty_bar : leader only, count 8 (4 epilogue warps of each CTA)
-constexpr int kPairStages = 6;
-constexpr int kPairStageBytes = kATileBytes + 128 * kBK * 2;      // 32 KB per CTA
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const KParams p) {
-  constexpr int BN = 256;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  __shared__ __align__(8) uint64_t full_bar[kPairStages];
-  __shared__ __align__(8) uint64_t empty_bar[kPairStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_stats[2 * kMaxCout];
-  __shared__ float s_bias[kMaxCout];
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int per_class = p.m_tiles * p.n_tiles;            // m_tiles counts 256-pixel tiles here
-  const int num_tiles = per_class * p.cls.n;
-  const int cout = p.n_tiles * BN;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < kPairStages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 8);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tmem_alloc_pair(smem_u32(&tmem_base_slot), 2 * BN);
-    tmem_relinquish_pair();
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < cout; i += 128) s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
-    if (p.e.stats)
-      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) s_stats[i] = 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                      // the peer's barriers are initialised before anything targets them
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      const int hw = p.GH * p.GW;
-      uint32_t kbg = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int cls = tile / per_class, t_in = tile - cls * per_class;
-        const int m0 = (t_in / p.n_tiles) * 256 + static_cast<int>(rank) * kBM;
-        const int n0 = (t_in % p.n_tiles) * BN + static_cast<int>(rank) * 128;
-        const int n_img = m0 / hw;
-        const int rem = m0 - n_img * hw;
-        const int gh = rem / p.GW;
-        const int gw = rem - gh * p.GW;
-        const int cw = gw * p.trav_stride + p.lower_w;
-        const int ch = gh * p.trav_stride + p.lower_h;
-        for (int tap = p.cls.tap_begin[cls]; tap < p.cls.tap_begin[cls] + p.cls.tap_count[cls]; ++tap) {
-          for (int cb = 0; cb < p.cin_blocks; ++cb, ++kbg) {
-            const uint32_t s = kbg % kPairStages;
-            const uint32_t round = kbg / kPairStages;
-            mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);
-            const uint32_t fb = smem_u32(&full_bar[s]);
-            if (rank == 0) mbar_expect_tx(fb, 2 * kPairStageBytes);
-            const uint32_t a_dst = smem_u32(smem + s * kPairStageBytes);
-            const uint32_t b_dst = a_dst + kATileBytes;
-            tma_load_im2col_4d_pair(a_dst, &tmap_a, fb, cb * kBK, cw, ch, n_img, p.taps.off_w[tap],
-                                    p.taps.off_h[tap]);
-            tma_load_2d_pair(b_dst, &tmap_b, fb, p.taps.k_off[tap] + cb * kBK, n0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
-      uint32_t kbg = 0, it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-        const uint32_t acc = it & 1, use = it >> 1;
-        const int num_kb = p.cls.tap_count[tile / per_class] * p.cin_blocks;
-        mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
-          const uint32_t s = kbg % kPairStages;
-          const uint32_t round = kbg / kPairStages;
-          mbar_wait(smem_u32(&full_bar[s]), round & 1);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(smem + s * kPairStageBytes);
-            const uint32_t b_addr = a_addr + kATileBytes;
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
-              const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_bf16_pair(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit_pair(smem_u32(&empty_bar[s]));
-            if (kb == num_kb - 1) umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue (both CTAs, own 128 lanes)
-    const int quad = warp & 3;
-    const int hw = p.GH * p.GW;
-    const float slope = resolve_slope(p.e);
-    uint32_t it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const uint32_t acc = it & 1, use = it >> 1;
-      const int cls = tile / per_class, t_in = tile - cls * per_class;
-      const int n0 = (t_in % p.n_tiles) * BN;
-      const int row = (t_in / p.n_tiles) * 256 + static_cast<int>(rank) * kBM + quad * 32 + lane;
-      const bool valid = row < p.M;
-      const int rr = valid ? row : 0;
-      const int n_img = rr / hw;
-      const int rem = rr - n_img * hw;
-      const int gh = rem / p.GW;
-      const int gw = rem - gh * p.GW;
-      mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
-      tc_fence_after();
-      epilogue_tile<BN>(p.e, tmem_base + acc * BN, quad, lane, n0, cout, n_img, gh, gw, valid, slope,
-                        s_bias, s_stats, p.cls.opy[cls], p.cls.opx[cls]);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(smem_u32(&tmem_empty_bar[acc]));
-    }
-    if (p.e.stats) flush_stats(p.e, s_stats, cout);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                      // no MMA of the leader still reads this CTA's shared memory
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, 2 * BN);
-  }
-}
-
 // ------------------------------------------------------------------ transposed kernel (Cout <= 128)
 constexpr int kTP = 256;                          // pixels per tile (UMMA N)
 constexpr int kTWBytes = 128 * kBK * 2;           // weight tile: 128 rows x 64 k
@@ -793,182 +608,6 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmap_px, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------ halo-fed kernel
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
-igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const HParams p) {
-  constexpr int kBTile = BN * kBK * 2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_b = smem + 2 * kHaloABytes;
-  __shared__ __align__(8) uint64_t a_full[2];
-  __shared__ __align__(8) uint64_t a_empty[2];
-  __shared__ __align__(8) uint64_t b_full[STAGES];
-  __shared__ __align__(8) uint64_t b_empty[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_stats[2 * kMaxCout];
-  __shared__ float s_bias[kMaxCout];
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
-  const int cout = p.n_tiles * BN;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&b_full[s]), 1);
-      mbar_init(smem_u32(&b_empty[s]), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&a_full[i]), 1);
-      mbar_init(smem_u32(&a_empty[i]), 1);
-      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_slot), 2 * BN);
-    tmem_relinquish();
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < cout; i += 128) s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
-    if (p.e.stats)
-      for (int i = threadIdx.x - 64; i < 2 * cout; i += 128) s_stats[i] = 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      if (p.resident) {   // the whole [Cout, 9*64] weight matrix: nine B tiles, loaded once
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t fb = smem_u32(&b_full[tap]);
-          mbar_expect_tx(fb, kBTile);
-          tma_load_2d(smem_u32(smem_b + tap * kBTile), &tmap_b, fb, p.k_off[tap], 0);
-        }
-      }
-      uint32_t ub = 0, kbg = 0;   // A-box counter, B-stage counter (pipeline phases)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tile_m = tile / p.n_tiles;
-        const int n0 = (tile % p.n_tiles) * BN;
-        const int n_img = tile_m / p.tiles_hw;
-        const int r2 = tile_m - n_img * p.tiles_hw;
-        const int h0 = (r2 / p.tiles_w) * p.R;
-        const int w0 = (r2 % p.tiles_w) * p.TW;
-        for (int cb = 0; cb < p.cin_blocks; ++cb, ++ub) {
-          const uint32_t ab = ub & 1;
-          mbar_wait(smem_u32(&a_empty[ab]), ((ub >> 1) & 1) ^ 1);
-          const uint32_t fa = smem_u32(&a_full[ab]);
-          mbar_expect_tx(fa, p.a_bytes);
-          tma_load_4d(smem_u32(smem + ab * kHaloABytes), &tmap_a, fa, cb * kBK, w0 - 1, h0 - 1, n_img);
-          if (!p.resident) {
-            for (int tap = 0; tap < 9; ++tap, ++kbg) {
-              const uint32_t s = kbg % STAGES;
-              mbar_wait(smem_u32(&b_empty[s]), ((kbg / STAGES) & 1) ^ 1);
-              const uint32_t fb = smem_u32(&b_full[s]);
-              mbar_expect_tx(fb, kBTile);
-              tma_load_2d(smem_u32(smem_b + s * kBTile), &tmap_b, fb, p.k_off[tap] + cb * kBK, n0);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
-    uint32_t ub = 0, kbg = 0, it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1, use = it >> 1;
-      mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int cb = 0; cb < p.cin_blocks; ++cb, ++ub) {
-        const uint32_t ab = ub & 1;
-        mbar_wait(smem_u32(&a_full[ab]), (ub >> 1) & 1);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + ab * kHaloABytes);
-        for (int tap = 0; tap < 9; ++tap) {
-          uint32_t s, parity;
-          if (p.resident) {
-            s = tap;
-            parity = 0;
-          } else {
-            s = kbg % STAGES;
-            parity = (kbg / STAGES) & 1;
-          }
-          mbar_wait(smem_u32(&b_full[s]), parity);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_tap = a_addr + p.shift[tap] * 128;
-            const uint32_t b_addr = smem_u32(smem_b + s * kBTile);
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t da = umma_smem_desc(a_tap + k * 32, 16, 1024);
-              const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_bf16(tmem_d, da, db, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            }
-            if (!p.resident) umma_commit(smem_u32(&b_empty[s]));
-          }
-          __syncwarp();
-          if (!p.resident) ++kbg;
-        }
-        if (lane == 0) {
-          umma_commit(smem_u32(&a_empty[ab]));
-          if (cb == p.cin_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue
-    const int quad = warp & 3;
-    const float slope = resolve_slope(p.e);
-    const int i = quad * 32 + lane;        // accumulator row = r * PW + c
-    const int r = i / p.PW, c = i - r * p.PW;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1, use = it >> 1;
-      const int tile_m = tile / p.n_tiles;
-      const int n0 = (tile % p.n_tiles) * BN;
-      const int n_img = tile_m / p.tiles_hw;
-      const int r2 = tile_m - n_img * p.tiles_hw;
-      int gh = (r2 / p.tiles_w) * p.R + r;
-      int gw = (r2 % p.tiles_w) * p.TW + c;
-      const bool valid = c < p.TW && r < p.R && gh < p.H && gw < p.W;
-      if (!valid) gh = gw = 0;
-      mbar_wait(smem_u32(&tmem_full_bar[acc]), use & 1);
-      tc_fence_after();
-      epilogue_tile<BN>(p.e, tmem_base + acc * BN, quad, lane, n0, cout, n_img, gh, gw, valid, slope,
-                        s_bias, s_stats, p.e.opy, p.e.opx);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-    }
-    if (p.e.stats) flush_stats(p.e, s_stats, cout);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
-  }
-}
-
-int g_pair = [] { const char* e = getenv("SISR_PAIR"); return e && e[0] == '1' ? 1 : 0; }();
-int g_pdl = [] { const char* e = getenv("SISR_PDL"); return e && e[0] == '1' ? 1 : 0; }();
 
 template <typename K, typename P>
 int launch_kernel(K kernel, bool* configured, int smem_bytes, const CUtensorMap& ta, const CUtensorMap& tb,
@@ -981,23 +620,7 @@ int launch_kernel(K kernel, bool* configured, int smem_bytes, const CUtensorMap&
     }
     *configured = true;
   }
-  if (g_pdl) {
-    // the prologue (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the
-    // previous kernel in the stream; every kernel of this file calls pdl_wait() before touching memory
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, ta, tb, kp);
-  } else {
-    kernel<<<grid, threads, smem_bytes, stream>>>(ta, tb, kp);
-  }
+  kernel<<<grid, threads, smem_bytes, stream>>>(ta, tb, kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "igemm launch: %s", cudaGetErrorString(e));
@@ -1013,16 +636,6 @@ int launch_im2col(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& k
   return launch_kernel(igemm_tc_kernel<BN, STAGES>, &configured, STAGES * SmemLayout<BN>::kStageBytes + 1024,
                        ta, tb, kp, grid, stream);
 }
-template <int BN, int STAGES>
-int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const HParams& hp, int grid,
-                cudaStream_t stream) {
-  static bool configured = false;
-  return launch_kernel(igemm_halo_kernel<BN, STAGES>, &configured,
-                       2 * kHaloABytes + STAGES * BN * kBK * 2 + 1024, ta, tb, hp, grid, stream);
-}
-
-int g_halo_mode = 0;   // 0: never (default: measured slower, see header), 1: cost model, 2: whenever the
-                       // geometry allows (tests)
 int g_transposed = 1;  // 1: Cout <= 128 layers run with the pixels on the UMMA N side
 int g_num_sms = 0;
 int num_sms() {
@@ -1047,7 +660,7 @@ double plan_cost(long long tiles, double bytes_per_tile, double mma_clk) {
 }
 
 struct Plan {
-  int halo, bn, tw, r, tiles_w, tiles_h, resident;
+  int bn;
   double cost;
 };
 
@@ -1058,45 +671,15 @@ Plan make_plan(const IgemmProblem& p) {
   const int m_tiles_i = static_cast<int>((M + kBM - 1) / kBM);
   const int cin_blocks = p.Cin / kBK;
   const int cands[3] = {256, 128, 64};
-  // halo geometry
-  bool halo_ok = g_halo_mode > 0 && p.n_classes <= 1 && p.trav_stride == 1 && p.GH == p.H && p.GW == p.W && p.num_taps == 9 &&
-                 p.lower_w == -1 && p.lower_h == -1;
-  for (int t = 0; halo_ok && t < 9; ++t) halo_ok = p.taps.off_w[t] <= 2 && p.taps.off_h[t] <= 2;
-  int tw = 0, r = 0, tiles_w = 0, tiles_h = 0;
-  if (halo_ok) {
-    long long best_tiles = 0;
-    for (int cw = 4; cw <= 61 && cw <= p.W; ++cw) {
-      int rr = (128 - cw) / (cw + 2) + 1;
-      if (rr > p.H) rr = p.H;
-      if ((cw + 2) * (rr + 2) * 128 > kHaloABytes) continue;
-      const int nw = (p.W + cw - 1) / cw, nh = (p.H + rr - 1) / rr;
-      const long long nt = static_cast<long long>(nw) * nh;
-      if (tw == 0 || nt < best_tiles || (nt == best_tiles && cw > tw)) {
-        tw = cw; r = rr; tiles_w = nw; tiles_h = nh; best_tiles = nt;
-      }
-    }
-    if (tw == 0) halo_ok = false;
-  }
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (p.Cout % bn) continue;
     if (p.ps_c > 0 && (p.ps_c % 32)) continue;
     const int n_tiles = p.Cout / bn;
     const double mma = 2.0 * bn * 9 * cin_blocks;
-    {
-      const double bytes = 9.0 * cin_blocks * (kATileBytes + bn * 128.0);
-      const double c = plan_cost(static_cast<long long>(m_tiles_i) * n_tiles, bytes, mma);
-      if (best.cost < 0 || c < best.cost) best = Plan{0, bn, 0, 0, 0, 0, 0, c};
-    }
-    if (halo_ok) {
-      const int stages = bn == 256 ? 4 : 9;
-      const int resident = (cin_blocks == 1 && n_tiles == 1 && stages >= 9) ? 1 : 0;
-      const double a_bytes = (tw + 2) * (r + 2) * 128.0;
-      const double bytes = cin_blocks * (a_bytes + (resident ? 0.0 : 9.0 * bn * 128.0));
-      double c = plan_cost(static_cast<long long>(p.NB) * tiles_h * tiles_w * n_tiles, bytes, mma);
-      if (g_halo_mode == 2) c = 0.0;
-      if (best.cost < 0 || c < best.cost) best = Plan{1, bn, tw, r, tiles_w, tiles_h, resident, c};
-    }
+    const double bytes = 9.0 * cin_blocks * (kATileBytes + bn * 128.0);
+    const double c = plan_cost(static_cast<long long>(m_tiles_i) * n_tiles, bytes, mma);
+    if (best.cost < 0 || c < best.cost) best = Plan{bn, c};
   }
   return best;
 }
@@ -1130,9 +713,7 @@ void fill_epi(EpiParams& e, const IgemmProblem& p) {
 
 const char* igemm_last_error() { return g_err; }
 int igemm_max_ctas() { return num_sms(); }
-void igemm_set_halo_mode(int mode) { g_halo_mode = mode; }
 void igemm_set_transposed(int on) { g_transposed = on; }
-void igemm_set_pair(int on) { g_pair = on; }
 
 bool igemm_supported(const IgemmProblem& p) {
   if (p.Cin % 64 || p.Cout % 64 || p.Cout > kMaxCout) return false;
@@ -1154,13 +735,13 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
              p.Cout, p.num_taps, p.ldc);
     return 1;
   }
-  if (g_halo_mode != 2 && igemm_th_supported(p)) {
+  if (igemm_th_supported(p)) {
     const int rc = igemm_th_launch(p, stream);
     if (rc) snprintf(g_err, sizeof g_err, "%s", igemm_th_last_error());
     return rc;
   }
   const bool flat_out = p.osy == 1 && p.osx == 1 && p.opy == 0 && p.opx == 0 && p.OH == p.GH && p.OW == p.GW;
-  if (g_transposed && p.Cout <= 128 && p.ps_c == 0 && flat_out && p.n_classes <= 1 && g_halo_mode != 2) {
+  if (g_transposed && p.Cout <= 128 && p.ps_c == 0 && flat_out && p.n_classes <= 1) {
     CUtensorMap tpx, tw;
     if (make_tmap_2d_bf16(&tw, p.w, p.Cout, p.Ktot, p.Ktot, kBK, 128)) {
       snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
@@ -1202,36 +783,6 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
     snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
     return 2;
   }
-  if (pl.halo) {
-    if (make_tmap_tiled_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, kBK, pl.tw + 2, pl.r + 2)) {
-      snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
-      return 2;
-    }
-    HParams hp;
-    hp.H = p.H; hp.W = p.W;
-    hp.TW = pl.tw; hp.R = pl.r; hp.PW = pl.tw + 2;
-    hp.tiles_w = pl.tiles_w; hp.tiles_hw = pl.tiles_w * pl.tiles_h;
-    hp.m_tiles = p.NB * hp.tiles_hw;
-    hp.n_tiles = p.Cout / bn;
-    hp.cin_blocks = p.Cin / kBK;
-    hp.a_bytes = hp.PW * (pl.r + 2) * 128;
-    hp.resident = pl.resident;
-    for (int t = 0; t < 9; ++t) {
-      hp.shift[t] = p.taps.off_h[t] * hp.PW + p.taps.off_w[t];
-      hp.k_off[t] = p.taps.k_off[t];
-    }
-    fill_epi(hp.e, p);
-    const int tiles = hp.m_tiles * hp.n_tiles;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    switch (bn) {
-      case 64:
-        return launch_halo<64, 9>(ta, tb, hp, grid, stream);
-      case 128:
-        return launch_halo<128, 9>(ta, tb, hp, grid, stream);
-      default:
-        return launch_halo<256, 4>(ta, tb, hp, grid, stream);
-    }
-  }
   if (make_tmap_im2col_nhwc_bf16(&ta, p.x, p.NB, p.H, p.W, p.Cin, p.lower_w, p.lower_h, p.upper_w,
                                  p.upper_h, kBK, kBM, p.trav_stride)) {
     snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
@@ -1254,21 +805,6 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   fill_epi(kp.e, p);
   const int tiles = kp.m_tiles * kp.n_tiles * kp.cls.n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (g_pair && bn == 256 && num_sms() >= 2) {
-    // CTA-pair kernel (round-2 draft, off by default): 256-pixel tiles, the weight tile split across the pair
-    CUtensorMap tb2;
-    if (make_tmap_2d_bf16(&tb2, p.w, p.Cout, p.Ktot, p.Ktot, kBK, 128)) {
-      snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
-      return 2;
-    }
-    kp.m_tiles = static_cast<int>((M + 255) / 256);
-    const int ptiles = kp.m_tiles * kp.n_tiles * kp.cls.n;
-    int pairs = num_sms() / 2;
-    if (ptiles < pairs) pairs = ptiles;
-    static bool configured = false;
-    return launch_kernel(igemm_pair_kernel, &configured, kPairStages * kPairStageBytes + 1024, ta, tb2, kp,
-                         2 * pairs, stream, kThreads);
-  }
   switch (bn) {
     case 64:
       return launch_im2col<64, 8>(ta, tb, kp, grid, stream);

@@ -467,11 +467,8 @@ __global__ void dhead_tail_bwd_kernel(const float* __restrict__ h, const float* 
   if (threadIdx.x == 0) atomicAdd(db2, dz);
 }
 
-// first-generation GEMMs on request (A/B): SISR_HEAD_V1=1
-bool head_v1() {
-  static const bool v = [] { const char* e = getenv("SISR_HEAD_V1"); return e && e[0] == '1'; }();
-  return v;
-}
+// (the generic gemm_mma_kernel remains the fallback for head sizes the streaming kernels do not take)
+constexpr bool head_v1() { return false; }
 
 }  // namespace
 

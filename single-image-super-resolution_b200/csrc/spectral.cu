@@ -578,8 +578,7 @@ int weight_grad_reduce_finish(const float* partials, int splits, const float* w,
   }
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   const long long slabs = static_cast<long long>(Cout) * (Cin / 64);
-  static const int force_small = getenv("SISR_DIAG_FINISH_SMALL") ? 1 : 0;   // A-B timing
-  const bool small = slabs < 512 || force_small;      // trunk-sized layers: parallelism over coalescing
+  const bool small = slabs < 512;      // trunk-sized layers: parallelism over coalescing
   auto kernel = small ? wgrad_reduce_finish_small_kernel : wgrad_reduce_finish_kernel;
   long long want = small ? (total / 4 + 15) / 16 : slabs;
   if (!sigma) {   // no gradient through sigma: phase 1 alone is complete

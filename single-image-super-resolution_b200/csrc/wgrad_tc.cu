@@ -28,8 +28,8 @@ constexpr int kPix = 64;                      // pixels per k-block
 constexpr int kTile = kPix * 64 * 2;          // 8 KB
 constexpr int kSlots = 11;                    // 9 taps + 1 unused (pair of tap 8) + dY
 constexpr int kStageBytes = kSlots * kTile;   // 88 KB
-constexpr int kStages = 2;                    // (32-pixel k-blocks x 4 stages measured no faster: the ten
-                                              // im2col loads per k-block are TMA-throughput bound)
+constexpr int kStages = 2;                    // (32-pixel k-blocks x 4 stages and a halo-box feed measured no
+                                              // faster, profiles/r1_notes.md: bound by the N = 64 instruction floor)
 constexpr int kThreads = 192;
 constexpr int kPairs = 5;
 constexpr int kTmemCols = 512;
@@ -183,145 +183,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------ halo-fed variant (stride 1)
-// A k-block is R full image rows in a padded-flat order of pitch PW = W + 4 (columns -2 .. W+1).
-// ONE tiled TMA box {64 ci, PW, R+2} brings the rows with their halo and one box {64 co, PW, R} the
-// output gradient; columns outside the image are zero-filled by TMA, so the products of the four
-// padding columns vanish.  The nine taps are nine views of the x box: padded position i reads box
-// row i + ty*PW + tx (descriptor start-address shift; the two taps of an accumulator pair are joined
-// through the leading-dimension offset = their shift difference).  3.8x fewer bytes through the TMA
-// unit than ten im2col tiles per 64 pixels (the im2col variant is TMA-throughput bound, ncu t36).
-constexpr int kHaloMaxStages = 3;
-struct HWParams {
-  int R, PW;
-  int units_per_img, total_units, units_per_split, splits;
-  int ci_blocks, co_blocks, Cin, Cout;
-  int k_steps;                   // 16-pixel MMA steps per unit: ceil(R * PW / 16)
-  int x_bytes, dy_bytes;         // bytes of the two TMA boxes
-  int x_alloc, stage_bytes, stages;
-  int shift[10];                 // box row shift of each tap (tap 9: padding of the last pair)
-  float* out;
-};
-
-__global__ void __launch_bounds__(kThreads, 1)
-wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
-                  const HWParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  __shared__ __align__(8) uint64_t full_bar[kHaloMaxStages];
-  __shared__ __align__(8) uint64_t empty_bar[kHaloMaxStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
-  __shared__ uint32_t tmem_base_slot;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  int b = blockIdx.x;
-  const int split = b % p.splits;
-  b /= p.splits;
-  const int cob = b % p.co_blocks;
-  const int cib = b / p.co_blocks;
-  const int u0 = split * p.units_per_split;
-  const int u1 = min(p.total_units, u0 + p.units_per_split);
-  const int num_units = u1 - u0;
-
-  // rows of the buffers that no TMA box covers are read by the MMAs (against zero gradients or into
-  // discarded products): they must hold finite values
-  for (int i = threadIdx.x; i < p.stages * p.stage_bytes / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async_smem();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_x);
-    tma_prefetch_desc(&tmap_dy);
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
-    }
-    mbar_init(smem_u32(&tmem_full_bar), 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < num_units; ++i) {
-        const int s = i % p.stages;
-        const uint32_t round = i / p.stages;
-        mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, p.x_bytes + p.dy_bytes);
-        const int u = u0 + i;
-        const int n_img = u / p.units_per_img;
-        const int h0 = (u - n_img * p.units_per_img) * p.R;
-        const uint32_t base = smem_u32(smem + s * p.stage_bytes);
-        tma_load_4d(base, &tmap_x, fb, cib * 64, -3, h0 - 1, n_img);
-        tma_load_4d(base + p.x_alloc, &tmap_dy, fb, cob * 64, -2, h0, n_img);
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
-    for (int i = 0; i < num_units; ++i) {
-      const int s = i % p.stages;
-      const uint32_t round = i / p.stages;
-      mbar_wait(smem_u32(&full_bar[s]), round & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t base = smem_u32(smem + s * p.stage_bytes);
-        const uint32_t dy_addr = base + p.x_alloc;
-        for (int j = 0; j < p.k_steps; ++j) {
-          const uint64_t db = umma_smem_desc(dy_addr + j * 2048, 4096, 1024);
-#pragma unroll
-          for (int q = 0; q < kPairs; ++q) {
-            const int s0 = p.shift[2 * q], s1 = p.shift[2 * q + 1];
-            const uint64_t da = umma_smem_desc(base + s0 * 128 + j * 2048, (s1 - s0) * 128, 1024);
-            umma_bf16(tmem_base + q * 64, da, db, idesc, (i > 0 || j > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(smem_u32(&empty_bar[s]));
-        if (i == num_units - 1) umma_commit(smem_u32(&tmem_full_bar));
-      }
-      __syncwarp();
-    }
-  } else {
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;          // accumulator row: tap parity * 64 + ci
-    const int ci = cib * 64 + (row & 63);
-    mbar_wait(smem_u32(&tmem_full_bar), 0);
-    tc_fence_after();
-    float* outp = p.out + static_cast<size_t>(split) * p.Cout * 9 * p.Cin;
-#pragma unroll 1
-    for (int q = 0; q < kPairs; ++q) {
-      const int tap = 2 * q + (row >> 6);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + q * 64 + c * 32, raw);
-        tmem_ld_wait();
-        if (tap < 9) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int co = cob * 64 + c * 32 + i;
-            outp[(static_cast<size_t>(co) * 9 + tap) * p.Cin + ci] = __uint_as_float(raw[i]);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
 // out[i] = sum_k ws[k][i]: block = 16 float4 columns x 16 split lanes, so that a thread issues at
 // most ceil(splits/16) independent 16-byte loads (the partials are 20-150 MB in total: HBM-bound).
 __global__ void __launch_bounds__(256)
@@ -396,38 +257,13 @@ int g_wgrad_atomic = [] { const char* e = getenv("SISR_WGRAD_ATOMIC"); return e 
 
 struct Plan {
   int total_kb, splits, kb_per_split, tiles, atomic;
-  // halo variant (halo = 1): a "k-block" is one unit of R image rows
-  int halo, R, PW, k_steps, x_alloc, stage_bytes, stages, units_per_img;
 };
-int g_wgrad_halo = 0;   // measured no faster: the kernel is bound by the ~128-cycle floor of the M = 128,
-                        // N = 64 tcgen05.mma, not by operand traffic (t36-t38); kept for A-B timing
 Plan make_plan(int n, int oh, int ow, int cin, int cout, int stride = 0, int ps = 1) {
   Plan pl{};
   const long long M = static_cast<long long>(n) * oh * ow;
   pl.total_kb = static_cast<int>((M + kPix - 1) / kPix);
   pl.tiles = (cin / 64) * (cout / 64);
   double fixed_cost = 1.0;       // per-CTA prologue + partial write, in k-blocks (a k-block = 20 MMAs ~ 1.4 us)
-  if (g_wgrad_halo && stride == 1 && !ps && ow + 4 <= 256) {
-    const int PW = ow + 4;
-    for (int R = oh < 32 ? oh : 32; R >= 1; --R) {
-      const int k_steps = (R * PW + 15) / 16;
-      const int x_rows = (k_steps * 16 + 2 * PW + 3 + 7) / 8 * 8;
-      const int box_rows = (R + 2) * PW;
-      const int x_alloc = ((x_rows > box_rows ? x_rows : box_rows) * 128 + 1023) / 1024 * 1024;
-      const int dy_alloc = (k_steps * 16 * 128 + 1023) / 1024 * 1024;
-      const int stage = x_alloc + dy_alloc;
-      if (R + 2 > 256 || (stage > 66 * 1024 && R > 1)) continue;
-      if (stage > 100 * 1024) break;
-      pl.halo = 1; pl.R = R; pl.PW = PW; pl.k_steps = k_steps; pl.x_alloc = x_alloc;
-      pl.stage_bytes = stage;
-      pl.stages = 200 * 1024 / stage;
-      if (pl.stages > kHaloMaxStages) pl.stages = kHaloMaxStages;
-      pl.units_per_img = (oh + R - 1) / R;
-      pl.total_kb = n * pl.units_per_img;                 // units
-      fixed_cost = 1.0 * 4.0 / k_steps;                   // same fixed cost expressed in units
-      break;
-    }
-  }
   // split the pixel range so that tiles x splits fills whole waves of the 148 SMs: minimise
   // waves / splits (time of the slowest SM), ties go to fewer splits (less partial-sum traffic)
   int splits = 1;
@@ -438,7 +274,7 @@ Plan make_plan(int n, int oh, int ow, int cin, int cout, int stride = 0, int ps 
     const char* e = getenv("SISR_WGRAD_SPLIT_COST");
     return e ? atof(e) : 0.1;      // 0.02 -> 0.1: step 8.38 -> 8.21 ms (r2 sweep 0.02 / 0.1 / 0.2 / 0.4)
   }();
-  pl.atomic = (g_wgrad_atomic && !pl.halo && static_cast<long long>(cout) * 9 * cin <= kAtomicMaxFloats) ? 1 : 0;
+  pl.atomic = (g_wgrad_atomic && static_cast<long long>(cout) * 9 * cin <= kAtomicMaxFloats) ? 1 : 0;
   const double per_split = pl.atomic ? 0.03 : split_cost;     // no partial copy to write and read back
   const int max_splits = pl.total_kb < 148 ? pl.total_kb : 148;
   for (int sp = 1; sp <= max_splits; ++sp) {
@@ -461,7 +297,6 @@ Plan make_plan(int n, int oh, int ow, int cin, int cout, int stride = 0, int ps 
 }  // namespace
 
 const char* wgrad_tc_last_error() { return g_err; }
-void wgrad_tc_set_halo(int on) { g_wgrad_halo = on; }
 
 bool wgrad_tc_supported(int n, int h, int w, int cin, int oh, int ow, int cout, int k, int stride,
                         int pad, int ps_r) {
@@ -491,39 +326,6 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
     cudaMemsetAsync(workspace, 0, sizeof(float) * static_cast<size_t>(cout) * 9 * cin, s);
   if (splits_out) *splits_out = pl.atomic ? 1 : pl.splits;
   CUtensorMap tx, tdy;
-  if (pl.halo) {
-    if (make_tmap_tiled_nhwc_bf16(&tx, x, n, h, w, cin, 64, pl.PW, pl.R + 2) ||
-        make_tmap_tiled_nhwc_bf16(&tdy, dy, n, oh, ow, cout, 64, pl.PW, pl.R)) {
-      snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
-      return 2;
-    }
-    HWParams hp;
-    hp.R = pl.R; hp.PW = pl.PW;
-    hp.units_per_img = pl.units_per_img;
-    hp.total_units = pl.total_kb;
-    hp.units_per_split = pl.kb_per_split;
-    hp.splits = pl.splits;
-    hp.ci_blocks = cin / 64; hp.co_blocks = cout / 64; hp.Cin = cin; hp.Cout = cout;
-    hp.k_steps = pl.k_steps;
-    hp.x_bytes = (pl.R + 2) * pl.PW * 128;
-    hp.dy_bytes = pl.R * pl.PW * 128;
-    hp.x_alloc = pl.x_alloc; hp.stage_bytes = pl.stage_bytes; hp.stages = pl.stages;
-    for (int t = 0; t < 9; ++t) hp.shift[t] = (t / 3) * pl.PW + (t % 3);
-    hp.shift[9] = hp.shift[8] + 1;
-    hp.out = (pl.splits > 1 || keep_partials) ? static_cast<float*>(workspace) : g;
-    const int smem_bytes = pl.stages * pl.stage_bytes + 1024;
-    static int configured = 0;
-    if (smem_bytes > configured) {
-      cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes);
-      if (e != cudaSuccess) {
-        snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        return 3;
-      }
-      configured = smem_bytes;
-    }
-    wgrad_halo_kernel<<<pl.tiles * pl.splits, kThreads, smem_bytes, s>>>(tx, tdy, hp);
-  } else {
   if (make_tmap_im2col_nhwc_bf16(&tx, x, n, h, w, cin, -1, -1, -1, -1, 64, kPix, stride)) {
     snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
     return 2;
@@ -559,8 +361,6 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
   }
   const int grid = pl.tiles * pl.splits;
   wgrad_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(tx, tdy, p);
-  }
-  const int ps = ps_r == 2;
   if (pl.splits > 1 && !keep_partials) {
     const long long total4 = static_cast<long long>(cout) * 9 * cin / 4;
     splitk_reduce_kernel<<<static_cast<int>((total4 + 15) / 16), 256, 0, s>>>(

@@ -17,6 +17,5 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
                     void* workspace, int n, int h, int w, int cin, int oh, int ow, int cout, int stride,
                     int ps_r, cudaStream_t s, int* splits_out = nullptr);
 const char* wgrad_tc_last_error();
-void wgrad_tc_set_halo(int on);   // 0: always the im2col-fed kernel (A-B timing)
 
 }  // namespace sisr

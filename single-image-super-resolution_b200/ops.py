@@ -34,7 +34,6 @@ _colsum_cache = {}
 # idempotent, so a gradient that reaches the producer through a second path is still handled right.
 _relu_outputs = {}
 _premasked = {}
-_NO_MASK_FUSION = bool(os.environ.get("SISR_DIAG_NO_MASK_FUSION"))     # A-B timing
 
 
 @contextlib.contextmanager
@@ -468,7 +467,6 @@ class Conv2dFn(torch.autograd.Function):
         ctx.weight_ref, ctx.bias_ref = weight, bias
         src = _relu_outputs.pop(x.data_ptr(), None)      # consumed by the one conv that reads this tensor
         ctx.input_is_relu = bool(src is not None and src.shape == x.shape and need_dx and not cfg.out_nchw_f32
-                                 and not _NO_MASK_FUSION
                                  and query("sisr_conv_dgrad_fuses_mask", d))
         if (cfg.act == ACT_RELU and need_dx and not cfg.out_nchw_f32 and cfg.ps_r != 2 and
                 (_skip_param_grads or not (weight.requires_grad or bias.requires_grad))):

@@ -87,10 +87,8 @@ def run(kind, name, h, cin, cout, stride, ps, stats):
 
 
 def main():
-    if os.environ.get("HALO_MODE"):
-        _lib.query("sisr_debug_halo_mode", int(os.environ["HALO_MODE"]))
-    if os.environ.get("WGRAD_HALO"):
-        _lib.query("sisr_debug_wgrad_halo", int(os.environ["WGRAD_HALO"]))
+    if os.environ.get("TH_MODE"):
+        _lib.query("sisr_debug_th_mode", int(os.environ["TH_MODE"]))
     if os.environ.get("TRANSPOSED"):
         _lib.query("sisr_debug_transposed", int(os.environ["TRANSPOSED"]))
     kinds = ["fprop", "dgrad", "wgrad"] if len(sys.argv) < 2 or sys.argv[1] == "all" else [sys.argv[1]]

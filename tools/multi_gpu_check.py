@@ -55,19 +55,22 @@ def main():
     tr = build(dev, parallel.GradSync(bucket_bytes=1 << 20))
     sl = slice(rank * per, (rank + 1) * per)
     def flat_grads(t, dp):
-        """Flattened gradients the optimizers consumed in the last step (dp: all-reduced bucket views / world)."""
+        """Flattened gradients the optimizers consumed in the last step (dp: all-reduced bucket views / world);
+        also per parameter, for the diagnostics below."""
         out = {}
         for name, net, opt in (("G", t.net_g, t.opt_g), ("D", t.net_d, t.opt_d)):
             gs = []
-            for q in net.parameters():
+            for pname, q in net.named_parameters():
                 if not q.requires_grad:
                     continue
                 if dp:
-                    gs.append((opt.grad_views[q] / world).flatten())
+                    g_ = (opt.grad_views[q] / world).flatten()
                 elif q.grad is not None:
-                    gs.append(q.grad.flatten())
+                    g_ = q.grad.flatten()
                 else:
-                    gs.append(torch.zeros(q.numel(), device=dev))
+                    g_ = torch.zeros(q.numel(), device=dev)
+                gs.append(g_)
+                out[name + ":" + pname] = g_.double().clone()
             out[name] = torch.cat(gs).double()
         return out
 
@@ -105,6 +108,20 @@ def main():
             cosine = float(a @ b / (a.norm() * b.norm()).clamp_min(1e-30))
             ratio = float(a.norm() / b.norm().clamp_min(1e-30))
             print(f"step-1 gradient {name}: cosine {cosine:.5f}  norm ratio {ratio:.4f}", flush=True)
+            # which parameters carry the difference: share of the squared difference per parameter
+            diffs = []
+            tot = float((a - b).pow(2).sum().clamp_min(1e-300))
+            for k in g_dp:
+                if k.startswith(name + ":"):
+                    da, db = g_dp[k], g_1p[k]
+                    diffs.append((float((da - db).pow(2).sum()) / tot, k, float(da.norm()), float(db.norm()), da.numel()))
+            for share, k, na, nb, numel in sorted(diffs, reverse=True)[:6]:
+                print(f"    {share * 100:5.1f} % of |dp - 1p|^2 in {k} (numel {numel}): |dp| {na:.4g}  |1p| {nb:.4g}", flush=True)
+            vec = [k for k in g_dp if k.startswith(name + ":") and g_dp[k].numel() > 1]
+            av, bv = torch.cat([g_dp[k] for k in vec]), torch.cat([g_1p[k] for k in vec])
+            cos_v = float(av @ bv / (av.norm() * bv.norm()).clamp_min(1e-30))
+            print(f"    without the scalar (PReLU slope) gradients: cosine {cos_v:.5f}  norm ratio "
+                  f"{float(av.norm() / bv.norm().clamp_min(1e-30)):.4f}", flush=True)
             ok &= cosine > 0.98 and abs(ratio - 1.0) < 0.05
         worst = 0.0
         for (k, a), (_, b) in zip(tr.net_g.state_dict().items(), ref.net_g.state_dict().items()):
