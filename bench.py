@@ -637,6 +637,24 @@ def run_ours(args):
         sustained = {"seconds": float(t_) * 1e-3, "steps": n_sus, "ms_per_step": ms_sus,
                      "value": batch * world / (ms_sus * 1e-3), "unit": "patches/s",
                      "clocks": sampler.window(ws0 + 1.0, ws1) if rank == 0 else None}
+    # ---- the graph path with replayed fakes (train.py:144-146: after 100 iterations int(len * 0.01) old fake
+    # batches join every D update; one CUDA graph per count k, captured on first use)
+    replay_path = None
+    if world == 1 and use_graph and args.config == "x4" and not args.no_replay_path:
+        replay_path = {}
+        for k in (1, 10):
+            olds = [(torch.rand((batch, 3, HR, HR), device=dev) * 2 - 1).to(torch.bfloat16) for _ in range(k)]
+            tr.replay(hr, lr, old_fakes=olds)                    # captures the k-fake graph, then replays it
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(10):
+                tr.replay(hr, lr, old_fakes=olds)
+            r1.record()
+            barrier()
+            replay_path[f"k={k}"] = {"ms_per_step": r0.elapsed_time(r1) / 10,
+                                     "d_passes_per_step": 3 + k}
+            del olds
     if rank == 0:
         sampler.stop()
     dp = dp_check(dev, rank, world, tr) if (world > 1 or os.environ.get("SISR_WRITE_DP_GOLDEN")) else None
@@ -679,6 +697,7 @@ def run_ours(args):
         "step_frac_of_sustained_bf16": cfg["flop"] * batch / (ms / args.steps * 1e-3) / 1e12
         / peaks["bf16_sustained"],
         "sustained": sustained,
+        "replay_path": replay_path,
         "losses": [float(x) for x in losses],
         "dp_check": dp,
         "clocks": clocks,
@@ -736,6 +755,8 @@ def main():
     ap.add_argument("--config", default="x4", choices=sorted(CONFIGS),
                     help="x4 = BASELINE.json configs[1]/[2]; frozen = configs[3]; x8 = configs[4]")
     ap.add_argument("--sustained-seconds", type=float, default=5.0)
+    ap.add_argument("--no-replay-path", action="store_true",
+                    help="skip timing the CUDA-graph step with 1 and 10 replayed fakes")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
