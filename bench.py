@@ -472,17 +472,23 @@ def ncu_traffic():
 
 
 def dominant_share():
-    """igemm_t_kernel's share of the step's kernel time, read from the committed ncu launch-list summary."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_step_launches_b64_final_summary.txt")
-    try:
-        for ln in open(path):
-            if "igemm_t_kernel" in ln:
-                f = ln.split()
-                return (f"igemm_t_kernel = {f[2]} of the step's kernel time, {f[3]} launches "
-                        f"(ncu launch list profiles/r1_step_launches_b64_final.csv)")
-    except OSError:
-        pass
-    return "see profiles/r1_step_launches_b64_final_summary.txt"
+    """The dominant kernels' share of the step's serialised kernel time, read from the newest committed ncu
+    launch-list summary (tools/launch_summary.py over `ncu --metrics gpu__time_duration.sum`)."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_launches_b64*summary.txt")), reverse=True)
+    for path in paths:
+        try:
+            hits = [ln.split() for ln in open(path) if re_kernel(ln)]
+        except OSError:
+            continue
+        if hits:
+            parts = [f"{f[-1]} = {f[2]} of the step's kernel time, {f[3]} launches" for f in hits]
+            return "; ".join(parts) + f" (ncu launch list, {os.path.relpath(path, ROOT)})"
+    return "see profiles/"
+
+
+def re_kernel(line):
+    return any(k in line for k in ("igemm_t_kernel", "igemm_th_kernel"))
 
 
 def run_ours(args):
