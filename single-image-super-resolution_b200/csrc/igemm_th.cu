@@ -41,7 +41,7 @@ constexpr int kStageWords = 32 * (32 + 16);            // staging tile of one ha
 constexpr int kStageBytes = 2 * kStageWords * 4;
 
 struct THParams {
-  int H, W, R, PW, tiles_h, num_tiles;
+  int H, W, R, TW, PW, tiles_h, tiles_w, num_tiles;   // tile = R rows x TW columns, box pitch PW = TW + 2
   int n_total, chunks, chunk_n;     // accumulator columns, MMA instructions per group, columns per instruction
   int n_valid;                      // R * PW: positions that can hold a real pixel
   int box_bytes, box_alloc, nbox, dbuf;
@@ -56,6 +56,8 @@ struct THParams {
   const float* slope_ptr;
   float* stats;
   int stats_rows;
+  const __nv_bfloat16* mask;   // nullable, indexed like `out`: stored value = mask > 0 ? v : v * mask_slope
+  float mask_slope;            // (ReLU backward of the tensor this data gradient belongs to, fused into the store)
 };
 
 thread_local char g_err[256] = "";
@@ -135,11 +137,13 @@ igemm_th_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t bb = it % p.nbox, use = it / p.nbox;
         mbar_wait(smem_u32(&box_empty[bb]), (use & 1) ^ 1);
-        const int n_img = tile / p.tiles_h;
-        const int h0 = (tile - n_img * p.tiles_h) * p.R;
+        const int per_img = p.tiles_h * p.tiles_w;
+        const int n_img = tile / per_img;
+        const int t2 = tile - n_img * per_img;
+        const int h0 = (t2 / p.tiles_w) * p.R, w0 = (t2 % p.tiles_w) * p.TW;
         const uint32_t fb = smem_u32(&box_full[bb]);
         mbar_expect_tx(fb, p.box_bytes);
-        tma_load_4d(smem_u32(smem_box + bb * p.box_alloc), &tmap_x, fb, 0, -1, h0 - 1, n_img);
+        tma_load_4d(smem_u32(smem_box + bb * p.box_alloc), &tmap_x, fb, 0, w0 - 1, h0 - 1, n_img);
       }
     }
   } else if (warp == 1) {
@@ -196,8 +200,10 @@ igemm_th_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = p.dbuf ? (it & 1) : 0, ause = p.dbuf ? (it >> 1) : it;
-      const int n_img = tile / p.tiles_h;
-      const int h0 = (tile - n_img * p.tiles_h) * p.R;
+      const int per_img = p.tiles_h * p.tiles_w;
+      const int n_img = tile / per_img;
+      const int t2 = tile - n_img * per_img;
+      const int h0 = (t2 / p.tiles_w) * p.R, w0 = (t2 % p.tiles_w) * p.TW;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.n_total;
       int ready = 0;                                   // instruction chunks of this accumulator known complete
 #pragma unroll 1
@@ -215,8 +221,8 @@ igemm_th_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         // this lane's position of the chunk: output pixel and validity (same in every warp of the half)
         const int o = o0 + lane;
         const int r = o / p.PW, c = o - r * p.PW;
-        const bool ok = o < p.n_valid && c < p.W && h0 + r < p.H;
-        const int opix = ok ? (n_img * p.H + h0 + r) * p.W + c : -1;
+        const bool ok = o < p.n_valid && c < p.TW && w0 + c < p.W && h0 + r < p.H;
+        const int opix = ok ? (n_img * p.H + h0 + r) * p.W + w0 + c : -1;
         const uint32_t vmask = __ballot_sync(0xffffffffu, ok);
         tmem_ld_wait();
         if (!is_lo) {
@@ -249,14 +255,34 @@ igemm_th_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             stage[(i + (odd ? 1 : 0)) * row_words + (co >> 1)] = word;
           }
           asm volatile("bar.sync %0, 64;" ::"r"(bar_stage) : "memory");
+          int pixk[4];
+          uint4 mk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int idx = tid_a + k * 64;
+            pixk[k] = __shfl_sync(0xffffffffu, opix, idx >> 3);
+            if (p.mask && pixk[k] >= 0)       // the four mask words of this thread's stores: loads issued together
+              mk[k] = __ldg(reinterpret_cast<const uint4*>(p.mask + static_cast<size_t>(pixk[k]) * p.ldc + (idx & 7) * 8));
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int idx = tid_a + k * 64;
             const int row = idx >> 3, seg = idx & 7;          // 8 16-byte segments per 64-channel pixel
-            const int pix = __shfl_sync(0xffffffffu, opix, row);
-            if (pix >= 0) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stage + row * row_words + seg * 4);
-              *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(pix) * p.ldc + seg * 8) = val;
+            if (pixk[k] >= 0) {
+              uint4 val = *reinterpret_cast<const uint4*>(stage + row * row_words + seg * 4);
+              if (p.mask) {
+                const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk[k]);
+                __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 mf = __bfloat1622float2(mh[j]);
+                  float2 vf = __bfloat1622float2(vh[j]);
+                  if (!(mf.x > 0.f)) vf.x *= p.mask_slope;
+                  if (!(mf.y > 0.f)) vf.y *= p.mask_slope;
+                  vh[j] = __floats2bfloat162_rn(vf.x, vf.y);
+                }
+              }
+              *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(pixk[k]) * p.ldc + seg * 8) = val;
             }
           }
         }
@@ -304,40 +330,49 @@ int sms() {
 }
 
 struct THPlan {
-  int R, n_total, chunks, chunk_n, box_alloc, nbox, dbuf, smem;
+  int R, TW, n_total, chunks, chunk_n, box_alloc, nbox, dbuf, smem;
   double cost;
 };
 
-// Rows per tile: minimise waves x (MMA cycles + epilogue + fixed) over the R that fit shared memory / TMEM.
+// Tile = R rows x TW columns: minimise waves x (MMA cycles + epilogue + fixed) over the shapes that fit shared
+// memory / TMEM.  Full-width tiles first (one box row = one image row); column tiles when an image row is too
+// wide for two box buffers beside the resident weights (VGG conv1_2 at 96 x 96).
 bool make_plan(const IgemmProblem& p, THPlan& best) {
-  const int PW = p.W + 2;
   best.cost = -1.0;
   const long long imgs = p.NB;
-  for (int R = 1; R <= p.H && R + 2 <= 256; ++R) {
-    int n_total = (R * PW + 15) / 16 * 16;
-    int chunks = 1;
-    if (n_total > 256) {
-      n_total = (R * PW + 31) / 32 * 32;
-      chunks = 2;
+  const int fixed = kGroups * kWTile + kXBytes + kStageBytes + 1024;
+  for (int split = 1; split <= 4; ++split) {
+    const int TW = (p.W + split - 1) / split;
+    if (TW + 2 > 256 || (split > 1 && TW < 16)) continue;
+    const int PW = TW + 2;
+    const int tiles_w = (p.W + TW - 1) / TW;
+    for (int R = 1; R <= p.H && R + 2 <= 256; ++R) {
+      int n_total = (R * PW + 15) / 16 * 16;
+      int chunks = 1;
+      if (n_total > 256) {
+        n_total = (R * PW + 31) / 32 * 32;
+        chunks = 2;
+      }
+      if (n_total > 512) break;
+      const int chunk_n = n_total / chunks;
+      const int rows_needed = n_total + 2 * PW + 2 > (R + 2) * PW ? n_total + 2 * PW + 2 : (R + 2) * PW;
+      const int box_alloc = (rows_needed * 128 + 1023) / 1024 * 1024;
+      const int tiles_h = (p.H + R - 1) / R;
+      const long long tiles = imgs * tiles_h * tiles_w;
+      const long long waves = (tiles + sms() - 1) / sms();
+      // several tiles per CTA need two box buffers (the load of tile i+1 under the MMAs of tile i): with one
+      // buffer VGG conv1_2 (96 x 96, 21 tiles per CTA) measured 130 us against 120 us on the im2col-fed kernel
+      const int nbox = waves > 1 ? 2 : 1;
+      if (fixed + nbox * box_alloc > 225 * 1024) continue;
+      if (waves > 1 && n_total < 192) continue;          // short instructions sit on the 94-cycle floor
+      const double mma = 4.0 * kGroups * chunks * (chunk_n * 0.5 + 38.0 > 94.0 ? chunk_n * 0.5 + 38.0 : 94.0);
+      const double epi = 14.0 * n_total;                 // TMEM reads, hand-over, transpose, stores
+      const double waste = 1.0 + 0.02 * (tiles_h * R - p.H) + 0.02 * (tiles_w * TW - p.W);
+      const double c = static_cast<double>(waves) * (mma + epi + 1500.0) * waste;
+      if (best.cost < 0 || c < best.cost)
+        best = THPlan{R, TW, n_total, chunks, chunk_n, box_alloc, nbox, 2 * n_total <= 512 ? 1 : 0,
+                      fixed + nbox * box_alloc, c};
     }
-    if (n_total > 512) break;
-    const int chunk_n = n_total / chunks;
-    const int rows_needed = n_total + 2 * PW + 2 > (R + 2) * PW ? n_total + 2 * PW + 2 : (R + 2) * PW;
-    const int box_alloc = (rows_needed * 128 + 1023) / 1024 * 1024;
-    const int tiles_h = (p.H + R - 1) / R;
-    const long long tiles = imgs * tiles_h;
-    const long long waves = (tiles + sms() - 1) / sms();
-    const int fixed = kGroups * kWTile + kXBytes + kStageBytes + 1024;
-    // several tiles per CTA need two box buffers (the load of tile i+1 under the MMAs of tile i): with one
-    // buffer VGG conv1_2 (96 x 96, 21 tiles per CTA) measured 130 us against 120 us on the im2col-fed kernel
-    const int nbox = waves > 1 ? 2 : 1;
-    if (fixed + nbox * box_alloc > 225 * 1024) continue;
-    if (waves > 1 && n_total < 192) continue;          // short instructions sit on the 94-cycle floor
-    const double mma = 4.0 * kGroups * chunks * (chunk_n * 0.5 + 38.0 > 94.0 ? chunk_n * 0.5 + 38.0 : 94.0);
-    const double epi = 14.0 * n_total;                 // TMEM reads, hand-over, transpose, stores
-    const double c = static_cast<double>(waves) * (mma + epi + 1500.0) * (1.0 + 0.02 * (tiles_h * R - p.H));
-    if (best.cost < 0 || c < best.cost)
-      best = THPlan{R, n_total, chunks, chunk_n, box_alloc, nbox, 2 * n_total <= 512 ? 1 : 0, fixed + nbox * box_alloc, c};
   }
   return best.cost >= 0;
 }
@@ -350,10 +385,11 @@ void igemm_set_th(int on) { g_th_mode = on; }
 // same-size stride-1 3x3 conv, 64 -> 64 channels, plain NHWC output, no fused gradient mask
 bool igemm_th_supported(const IgemmProblem& p) {
   if (!g_th_mode) return false;
-  if (p.Cin != 64 || p.Cout != 64 || p.num_taps != 9 || p.n_classes > 1 || p.ps_c != 0 || p.mask) return false;
+  if (p.Cin != 64 || p.Cout != 64 || p.num_taps != 9 || p.n_classes > 1 || p.ps_c != 0) return false;
+  if (p.mask && p.stats) return false;
   if (p.trav_stride != 1 || p.GH != p.H || p.GW != p.W || p.lower_w != -1 || p.lower_h != -1) return false;
   if (p.osy != 1 || p.osx != 1 || p.opy != 0 || p.opx != 0 || p.OH != p.GH || p.OW != p.GW) return false;
-  if (p.W + 2 > 256 || p.ldc % 8) return false;
+  if (p.ldc % 8) return false;
   if (p.stats && p.stats_rows < sms()) return false;
   int seen = 0;
   for (int t = 0; t < 9; ++t) {
@@ -372,16 +408,17 @@ int igemm_th_launch(const IgemmProblem& p, cudaStream_t stream) {
     return 1;
   }
   CUtensorMap tx, tw;
-  const int PW = p.W + 2;
+  const int PW = pl.TW + 2;
   if (make_tmap_2d_bf16(&tw, p.w, p.Cout, p.Ktot, p.Ktot, 64, 64) ||
       make_tmap_tiled_nhwc_bf16(&tx, p.x, p.NB, p.H, p.W, p.Cin, 64, PW, pl.R + 2)) {
     snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
     return 2;
   }
   THParams tp;
-  tp.H = p.H; tp.W = p.W; tp.R = pl.R; tp.PW = PW;
+  tp.H = p.H; tp.W = p.W; tp.R = pl.R; tp.TW = pl.TW; tp.PW = PW;
   tp.tiles_h = (p.H + pl.R - 1) / pl.R;
-  tp.num_tiles = p.NB * tp.tiles_h;
+  tp.tiles_w = (p.W + pl.TW - 1) / pl.TW;
+  tp.num_tiles = p.NB * tp.tiles_h * tp.tiles_w;
   tp.n_total = pl.n_total; tp.chunks = pl.chunks; tp.chunk_n = pl.chunk_n;
   tp.n_valid = pl.R * PW;
   tp.box_bytes = (pl.R + 2) * PW * 128;
@@ -400,6 +437,7 @@ int igemm_th_launch(const IgemmProblem& p, cudaStream_t stream) {
   tp.out = p.out; tp.ldc = p.ldc;
   tp.bias = p.bias; tp.act = p.act; tp.slope = p.slope; tp.slope_ptr = p.slope_ptr;
   tp.stats = p.stats; tp.stats_rows = p.stats_rows;
+  tp.mask = p.mask; tp.mask_slope = p.mask_slope;
   static int configured = 0;
   if (pl.smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(igemm_th_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);

@@ -1,0 +1,467 @@
+// Persistent, fused forward pass of the generator's 64-channel residual trunk (model_generator.py:5-19, 36-41,
+// 86-93): ALL conv3x3 -> train-mode BatchNorm -> PReLU / skip layers of the trunk in ONE cooperative launch.
+//
+// Why: unfused, every layer is three launches (conv 11.8 us + statistics finalize 3.5 us + normalise 3.7 us at
+// batch 64) on a 4.7 MB tensor that never leaves L2; the conv's tensor pipe is busy a quarter of its own
+// duration and the rest is launch, prologue, pipeline fill and drain.  Here one CTA per SM owns the same
+// R-row tile of one image in every layer (12 rows x 24 columns at 24 x 24), keeps TMEM, barriers and the
+// tensor maps alive across layers, and per layer does
+//   conv (the igemm_th scheme: stacked filter taps on M, pixels on N from one TMA box with halo)
+//   -> epilogue A: + bias, bf16 rounding, per-channel sums; the conv output y goes to global memory (the
+//      backward pass needs it) AND stays in shared memory
+//   -> grid barrier #1 (the per-CTA partial sums are visible)
+//   -> every CTA adds the partial rows in the same order -> batch mean / variance -> scale, shift
+//      (CTA 0 also stores them for the backward pass and updates the running statistics)
+//   -> pass B from shared memory: a = PReLU(scale * y + shift) or scale * y + shift + residual -> global
+//   -> grid barrier #2 (the neighbours' halo rows of `a` are visible) -> next layer.
+// The next layer's 72 KB of weights are fetched during pass B.  Train-mode statistics are a true batch-wide
+// dependency, so two grid barriers per layer are the floor of any fused design.
+// Single GPU only: with SyncBN the cross-GPU exchange would have to live inside barrier #1; the data-parallel
+// path keeps the per-layer kernels.
+#include <cooperative_groups.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "igemm.h"
+#include "ptx.cuh"
+#include "tmap.h"
+#include "trunk_fused.h"
+
+namespace sisr {
+
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int kWTile = 128 * 64 * 2;       // one stacked weight tile: 128 rows x 64 k
+constexpr int kGroups = 6;                 // 3 tap pairs + 3 single taps
+constexpr int kXRow = 33;                  // pitch (words) of the D_hi hand-over buffer
+constexpr int kXBytes = 2 * 64 * kXRow * 4;
+constexpr int kYPitch = 36;                // words per position of the y tile in shared memory (64 bf16 + pad)
+
+struct TrunkParams {
+  int NB, H, W, R, PW, tiles_h, num_tiles, n_layers;
+  int n_total, chunks, chunk_n, n_valid, box_bytes, box_alloc;
+  float count, momentum, eps;
+  int w_row_stride;                // rows of the weight matrix between consecutive layers
+  long long layer_elems;           // elements of one layer's activation tensor
+  __nv_bfloat16* y_all;            // [n_layers][NB, H, W, 64]: conv outputs (kept for the backward pass)
+  __nv_bfloat16* a_all;            // [n_layers][NB, H, W, 64]: layer outputs
+  float* partials;                 // [n_layers][grid][128]
+  unsigned int* barrier;           // zeroed before the launch
+  TrunkLayerDev layer[kTrunkMaxLayers];
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// All CTAs are co-resident (cooperative launch).  `target` = arrivals expected so far.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  fence_proxy_async_all();           // this thread's global stores -> later TMA (async proxy) reads elsewhere
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (clock64() - t0 > 4000000000LL) {
+        printf("sisr: trunk grid barrier timeout (block %d, target %u, seen %u)\n", blockIdx.x, target, seen);
+        __trap();
+      }
+    } while (seen < target);
+    __threadfence();
+    fence_proxy_async_all();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x0,
+                 const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TrunkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_box = smem + kGroups * kWTile;
+  float* xbuf = reinterpret_cast<float*>(smem_box + p.box_alloc);
+  uint32_t* ytile = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(xbuf) + kXBytes);   // [n_total][kYPitch]
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ __align__(8) uint64_t box_full;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_sum[2 * 64];
+  __shared__ float s_part[2][128];
+  __shared__ float s_scale[64], s_shift[64];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_img = blockIdx.x / p.tiles_h;
+  const int h0 = (blockIdx.x - n_img * p.tiles_h) * p.R;
+
+  // zero rows: upper halves of the single-tap weight tiles (groups 3..5) and the box rows behind the TMA box
+  for (int g = 3; g < kGroups; ++g)
+    for (int i = threadIdx.x; i < kWTile / 2 / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(smem_w + g * kWTile + kWTile / 2)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = p.box_bytes / 16 + threadIdx.x; i < p.box_alloc / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_box)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x0);
+    tma_prefetch_desc(&tmap_a);
+    mbar_init(smem_u32(&w_bar), 1);
+    mbar_init(smem_u32(&box_full), 1);
+    mbar_init(smem_u32(&tmem_full_bar[0]), 1);
+    mbar_init(smem_u32(&tmem_full_bar[1]), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // weights of layer l: rows [128 l, 128 l + 64) of the prepared-weight matrix, tap t at columns 64 t
+  auto load_weights = [&](int l) {
+    const uint32_t wb = smem_u32(&w_bar);
+    mbar_expect_tx(wb, 9 * (kWTile / 2));
+    for (int dy = 0; dy < 3; ++dy) {
+      tma_load_2d(smem_u32(smem_w + dy * kWTile), &tmap_w, wb, (dy * 3 + 0) * 64, l * p.w_row_stride);
+      tma_load_2d(smem_u32(smem_w + dy * kWTile + kWTile / 2), &tmap_w, wb, (dy * 3 + 1) * 64,
+                  l * p.w_row_stride);
+      tma_load_2d(smem_u32(smem_w + (3 + dy) * kWTile), &tmap_w, wb, (dy * 3 + 2) * 64,
+                  l * p.w_row_stride);
+    }
+  };
+  if (warp == 0 && lane == 0) load_weights(0);
+
+  unsigned int barriers_done = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const TrunkLayerDev& L = p.layer[l];
+    const uint32_t parity = l & 1;
+    __nv_bfloat16* const y_out = p.y_all + static_cast<size_t>(l) * p.layer_elems;
+    __nv_bfloat16* const a_out = p.a_all + static_cast<size_t>(l) * p.layer_elems;
+    // ------------------------------------------------------------------ conv
+    if (warp == 0) {
+      if (lane == 0) {
+        const uint32_t fb = smem_u32(&box_full);
+        mbar_expect_tx(fb, p.box_bytes);
+        // a_all is one [n_layers * NB, H, W, 64] tensor: layer l - 1, image n_img = index (l - 1) * NB + n_img
+        if (l == 0)
+          tma_load_4d(smem_u32(smem_box), &tmap_x0, fb, 0, -1, h0 - 1, n_img);
+        else
+          tma_load_4d(smem_u32(smem_box), &tmap_a, fb, 0, -1, h0 - 1, (l - 1) * p.NB + n_img);
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.chunk_n, 0, 0);
+      mbar_wait(smem_u32(&w_bar), parity);
+      mbar_wait(smem_u32(&box_full), parity);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t w_addr = smem_u32(smem_w), x_addr = smem_u32(smem_box);
+#pragma unroll 1
+        for (int c = 0; c < p.chunks; ++c) {
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+              const int sigma = g < 3 ? g * p.PW : (g - 3) * p.PW + 2;
+              const uint64_t da = umma_smem_desc(w_addr + g * kWTile + k * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc(x_addr + (sigma + c * p.chunk_n) * 128 + k * 32, 16, 1024);
+              umma_bf16(tmem_base + c * p.chunk_n, da, db, idesc, (k > 0 || g > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&tmem_full_bar[c]));
+        }
+      }
+      __syncwarp();
+    } else {
+      // -------------------------------------------------------------- epilogue A
+      const int quad = warp & 3;
+      const int half = (warp - 2) >> 2;
+      const bool is_lo = quad < 2;
+      const int co = (quad & 1) * 32 + lane;
+      const float bias = L.bias ? L.bias[co] : 0.f;
+      float* xb = xbuf + half * 64 * kXRow;
+      const int n_pchunks = (p.n_valid + 31) >> 5;
+      const int bar_full = 4 + half, bar_free = 6 + half;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      float s1 = 0.f, s2 = 0.f;
+      int ready = 0;
+      if (threadIdx.x - 64 < 128) s_sum[threadIdx.x - 64] = 0.f;
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+#pragma unroll 1
+      for (int pc = half; pc < n_pchunks; pc += 2) {
+        const int o0 = pc * 32;
+        int need = (o0 + 32) / p.chunk_n + 1;
+        if (need > p.chunks) need = p.chunks;
+        while (ready < need) {
+          mbar_wait(smem_u32(&tmem_full_bar[ready]), parity);
+          ++ready;
+        }
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld_32x32(trow + o0 + (is_lo ? 0 : 1), raw);
+        const int o = o0 + lane;
+        const int r = o / p.PW, c = o - r * p.PW;
+        const bool ok = o < p.n_valid && c < p.W && h0 + r < p.H;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, ok);
+        tmem_ld_wait();
+        if (!is_lo) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xb[co * kXRow + i] = __uint_as_float(raw[i]);
+          asm volatile("bar.arrive %0, 128;" ::"r"(bar_full) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_free) : "memory");
+        } else {
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_full) : "memory");
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = bf16_round(__uint_as_float(raw[i]) + xb[co * kXRow + i] + bias);
+            v[i] = x;
+            if ((vmask >> i) & 1u) {
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+          }
+          asm volatile("bar.arrive %0, 128;" ::"r"(bar_free) : "memory");
+          // transposed write into the y tile: a lane pair swaps one value per position pair, every thread
+          // writes packed {co, co+1} words (the tile keeps the whole layer output of this CTA)
+          const bool odd = lane & 1;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[i] : v[i + 1], 1);
+            const uint32_t word = odd ? pack_bf16x2(recv, v[i + 1]) : pack_bf16x2(v[i], recv);
+            ytile[(o0 + i + (odd ? 1 : 0)) * kYPitch + (co >> 1)] = word;
+          }
+        }
+      }
+      while (ready < p.chunks) {
+        mbar_wait(smem_u32(&tmem_full_bar[ready]), parity);
+        ++ready;
+      }
+      tc_fence_before();
+      if (is_lo) {
+        atomicAdd(&s_sum[co], s1);
+        atomicAdd(&s_sum[64 + co], s2);
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");       // y tile and the CTA's sums are complete
+      const int et = threadIdx.x - 64;                      // 0..255
+      if (et < 128) p.partials[(static_cast<size_t>(l) * gridDim.x + blockIdx.x) * 128 + et] = s_sum[et];
+      // y -> global (16 bytes per thread and step)
+      for (int item = et; item < p.n_valid * 8; item += 256) {
+        const int o = item >> 3, seg = item & 7;
+        const int r = o / p.PW, c = o - r * p.PW;
+        if (c < p.W && h0 + r < p.H) {
+          const size_t pix = static_cast<size_t>(n_img * p.H + h0 + r) * p.W + c;
+          *reinterpret_cast<uint4*>(y_out + pix * 64 + seg * 8) = *reinterpret_cast<const uint4*>(ytile + o * kYPitch + seg * 4);
+        }
+      }
+    }
+    grid_barrier(p.barrier, ++barriers_done * gridDim.x);
+
+    // ------------------------------------------------------------------ statistics -> scale / shift
+    if (warp == 0 && lane == 0 && l + 1 < p.n_layers) load_weights(l + 1);    // lands during pass B
+    if (threadIdx.x < 256) {
+      const int col = threadIdx.x & 127, rl = threadIdx.x >> 7;
+      const float* src = p.partials + static_cast<size_t>(l) * gridDim.x * 128 + col;
+      float acc = 0.f;
+      for (int r = rl; r < static_cast<int>(gridDim.x); r += 2) acc += __ldcg(src + static_cast<size_t>(r) * 128);
+      s_part[rl][col] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int c = threadIdx.x;
+      const float sum = s_part[0][c] + s_part[1][c], sq = s_part[0][64 + c] + s_part[1][64 + c];
+      const float mean = sum / p.count;
+      const float var = fmaxf(sq / p.count - mean * mean, 0.f);
+      const float invstd = rsqrtf(var + p.eps);
+      const float sc = L.gamma[c] * invstd;
+      const float sh = L.beta[c] - mean * sc;
+      s_scale[c] = sc;
+      s_shift[c] = sh;
+      if (blockIdx.x == 0) {
+        L.aux[c] = sc;
+        L.aux[64 + c] = sh;
+        L.aux[128 + c] = mean;
+        L.aux[192 + c] = invstd;
+        const float unbiased = p.count > 1.f ? var * p.count / (p.count - 1.f) : var;
+        L.running_mean[c] = (1.f - p.momentum) * L.running_mean[c] + p.momentum * mean;
+        L.running_var[c] = (1.f - p.momentum) * L.running_var[c] + p.momentum * unbiased;
+        if (c == 0 && L.nbt) *L.nbt += 1;
+      }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ pass B: normalise (+PReLU / +residual)
+    {
+      const float slope = L.slope ? __ldg(L.slope) : 1.f;
+      const __nv_bfloat16* res = L.residual;
+      for (int item = threadIdx.x; item < p.n_valid * 8; item += kThreads) {
+        const int o = item >> 3, seg = item & 7;
+        const int r = o / p.PW, c = o - r * p.PW;
+        if (!(c < p.W && h0 + r < p.H)) continue;
+        const size_t pix = static_cast<size_t>(n_img * p.H + h0 + r) * p.W + c;
+        uint4 val = *reinterpret_cast<const uint4*>(ytile + o * kYPitch + seg * 4);
+        uint4 rv = make_uint4(0, 0, 0, 0);
+        if (res) rv = *reinterpret_cast<const uint4*>(res + pix * 64 + seg * 8);
+        __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
+        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = seg * 8 + 2 * j;
+          float2 f = __bfloat1622float2(vh[j]);
+          f.x = fmaf(f.x, s_scale[ch], s_shift[ch]);
+          f.y = fmaf(f.y, s_scale[ch + 1], s_shift[ch + 1]);
+          if (L.slope) {
+            f.x = f.x > 0.f ? f.x : f.x * slope;
+            f.y = f.y > 0.f ? f.y : f.y * slope;
+          }
+          if (res) {
+            const float2 rr = __bfloat1622float2(rh[j]);
+            f.x += rr.x;
+            f.y += rr.y;
+          }
+          vh[j] = __floats2bfloat162_rn(f.x, f.y);
+        }
+        *reinterpret_cast<uint4*>(a_out + pix * 64 + seg * 8) = val;
+      }
+    }
+    grid_barrier(p.barrier, ++barriers_done * gridDim.x);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int g_sms = 0;
+int sms() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+thread_local char g_err[256] = "";
+
+struct Plan {
+  int R, n_total, chunks, chunk_n, box_alloc, smem, tiles_h, tiles;
+};
+
+bool make_plan(int nb, int h, int w, Plan& best) {
+  const int PW = w + 2;
+  double best_cost = -1.0;
+  if (PW > 256) return false;
+  for (int R = 1; R <= h && R + 2 <= 256; ++R) {
+    int n_total = (R * PW + 15) / 16 * 16, chunks = 1;
+    if (n_total > 256) {
+      n_total = (R * PW + 31) / 32 * 32;
+      chunks = 2;
+    }
+    if (n_total > 512) break;
+    const int chunk_n = n_total / chunks;
+    const int rows_needed = n_total + 2 * PW + 2 > (R + 2) * PW ? n_total + 2 * PW + 2 : (R + 2) * PW;
+    const int box_alloc = (rows_needed * 128 + 1023) / 1024 * 1024;
+    const int tiles_h = (h + R - 1) / R;
+    const long long tiles = static_cast<long long>(nb) * tiles_h;
+    if (tiles > sms()) continue;                        // every tile needs its own co-resident CTA
+    const int smem = kGroups * kWTile + box_alloc + kXBytes + n_total * kYPitch * 4 + 1024;
+    if (smem > 225 * 1024) continue;
+    const double mma = 4.0 * kGroups * chunks * (chunk_n * 0.5 + 38.0 > 94.0 ? chunk_n * 0.5 + 38.0 : 94.0);
+    const double cost = (mma + 14.0 * n_total + 1500.0) * (1.0 + 0.02 * (tiles_h * R - h));
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = Plan{R, n_total, chunks, chunk_n, box_alloc, smem, tiles_h, static_cast<int>(tiles)};
+    }
+  }
+  return best_cost >= 0;
+}
+
+}  // namespace
+
+const char* trunk_fused_last_error() { return g_err; }
+
+bool trunk_fused_supported(int nb, int h, int w, int n_layers) {
+  Plan pl;
+  int coop = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  return coop && n_layers >= 1 && n_layers <= kTrunkMaxLayers && make_plan(nb, h, w, pl);
+}
+
+size_t trunk_fused_workspace_bytes(int n_layers) {
+  return sizeof(float) * static_cast<size_t>(n_layers) * sms() * 128 + 256;
+}
+
+int trunk_fused_forward(const __nv_bfloat16* x0, int nb, int h, int w, const __nv_bfloat16* weights,
+                        int w_row_stride, const TrunkLayerHost* layers, int n_layers, __nv_bfloat16* y_all,
+                        __nv_bfloat16* a_all, float momentum, float eps, void* workspace, cudaStream_t stream) {
+  Plan pl;
+  if (!trunk_fused_supported(nb, h, w, n_layers) || !make_plan(nb, h, w, pl)) {
+    snprintf(g_err, sizeof g_err, "trunk_fused: unsupported geometry %d x %d x %d, %d layers", nb, h, w, n_layers);
+    return 1;
+  }
+  const int PW = w + 2;
+  CUtensorMap tw, tx0, ta;
+  if (make_tmap_2d_bf16(&tw, weights, static_cast<uint64_t>(n_layers - 1) * w_row_stride + 64, 576, 576, 64, 64) ||
+      make_tmap_tiled_nhwc_bf16(&tx0, x0, nb, h, w, 64, 64, PW, pl.R + 2) ||
+      make_tmap_tiled_nhwc_bf16(&ta, a_all, n_layers * nb, h, w, 64, 64, PW, pl.R + 2)) {
+    snprintf(g_err, sizeof g_err, "%s", tmap_last_error());
+    return 2;
+  }
+  TrunkParams p{};
+  p.NB = nb; p.H = h; p.W = w; p.R = pl.R; p.PW = PW;
+  p.tiles_h = pl.tiles_h; p.num_tiles = pl.tiles; p.n_layers = n_layers;
+  p.n_total = pl.n_total; p.chunks = pl.chunks; p.chunk_n = pl.chunk_n;
+  p.n_valid = pl.R * PW;
+  p.box_bytes = (pl.R + 2) * PW * 128;
+  p.box_alloc = pl.box_alloc;
+  p.count = static_cast<float>(nb) * h * w;
+  p.momentum = momentum; p.eps = eps;
+  p.w_row_stride = w_row_stride;
+  p.layer_elems = static_cast<long long>(nb) * h * w * 64;
+  p.y_all = y_all; p.a_all = a_all;
+  p.barrier = static_cast<unsigned int*>(workspace);
+  p.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  for (int l = 0; l < n_layers; ++l) {
+    const TrunkLayerHost& s = layers[l];
+    TrunkLayerDev& d = p.layer[l];
+    d.bias = s.bias; d.gamma = s.gamma; d.beta = s.beta;
+    d.running_mean = s.running_mean; d.running_var = s.running_var; d.nbt = s.nbt;
+    d.slope = s.slope; d.aux = s.aux;
+    if (s.residual_layer >= l) {
+      snprintf(g_err, sizeof g_err, "trunk_fused: layer %d takes its residual from a later layer", l);
+      return 1;
+    }
+    d.residual = s.residual_layer == -2 ? x0
+               : (s.residual_layer >= 0 ? a_all + static_cast<size_t>(s.residual_layer) * p.layer_elems : nullptr);
+  }
+  static int configured = 0;
+  if (pl.smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(trunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 3;
+    }
+    configured = pl.smem;
+  }
+  cudaMemsetAsync(workspace, 0, 256, stream);
+  void* args[] = {&tw, &tx0, &ta, &p};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(trunk_fwd_kernel), dim3(pl.tiles),
+                                              dim3(kThreads), args, pl.smem, stream);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof g_err, "trunk_fused launch: %s", cudaGetErrorString(e));
+    return 4;
+  }
+  return 0;
+}
+
+}  // namespace sisr

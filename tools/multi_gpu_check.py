@@ -24,7 +24,10 @@ def build(dev, grad_sync, seed=800, shape=(3, 32, 32), feats=(64, 64, 128, 128),
     for net, st in ((net_g, g_st), (net_d, d_st), (ext, v_st)):
         torch.nn.Module.load_state_dict(net, S.clone_state(st), strict=True)
     net_g, net_d, ext = net_g.to(dev), net_d.to(dev), ext.to(dev)
-    return m.SRGANTrainer(net_g, net_d, ext, m.StepConfig(lr=1e-5, use_replay=False), grad_sync=grad_sync)
+    cfg = m.StepConfig(lr=1e-5, use_replay=False,
+                       async_weight_grads=os.environ.get("MGC_ASYNC", "1") != "0",          # diagnostics
+                       overlap_real_features=os.environ.get("MGC_OVERLAP", "1") != "0")
+    return m.SRGANTrainer(net_g, net_d, ext, cfg, grad_sync=grad_sync)
 
 
 def main():
@@ -52,7 +55,45 @@ def main():
     per = 4
     hr_all = S.synthetic_hr(4321, per * world, 32)
     lr_all = F.interpolate(hr_all, (8, 8), mode="bicubic", align_corners=True).clamp(-1, 1)
-    tr = build(dev, parallel.GradSync(bucket_bytes=1 << 20))
+    # 1b. SyncBN forward + backward in isolation (no NCCL, no side streams): a chain of BatchNorm layers on
+    # per-rank shards against one process on the concatenated batch
+    from sisr_b200.ops import BnActFn, BnCfg, ACT_PRELU
+    gen = torch.Generator().manual_seed(99)
+    xs = (torch.randn(world * 4, 8, 8, 64, generator=gen) * 1.5 + 0.3).to(torch.bfloat16)
+    gs = torch.randn(world * 4, 8, 8, 64, generator=gen).to(torch.bfloat16)
+
+    def bn_chain(x, g, sync):
+        x = x.to(dev).requires_grad_(True)
+        gam = torch.full((64,), 1.2, device=dev, requires_grad=True)
+        bet = torch.full((64,), 0.1, device=dev, requires_grad=True)
+        slope = torch.full((1,), 0.25, device=dev, requires_grad=True)
+        h = x
+        ops.begin_step(dev)
+        with (ops.sync_bn_scope() if sync else __import__("contextlib").nullcontext()):
+            for _ in range(6):
+                rm, rv = torch.zeros(64, device=dev), torch.ones(64, device=dev)
+                h = BnActFn.apply(h, None, gam, bet, rm, rv, torch.zeros((), dtype=torch.long, device=dev), None, slope,
+                                  BnCfg(act=ACT_PRELU, training=True))
+            h.backward(g.to(dev))
+        torch.cuda.synchronize()
+        return h.detach().float(), x.grad.float(), gam.grad.clone()
+    sl4 = slice(rank * 4, (rank + 1) * 4)
+    out_dp, dx_dp, dgam_dp = bn_chain(xs[sl4], gs[sl4], True)
+    dist.all_reduce(dgam_dp)
+    if rank == 0:
+        keep = (ops._dist_group, ops._peer)
+        ops.set_sync_group(None)
+        ops.set_peer_exchange(None)
+        out_1p, dx_1p, dgam_1p = bn_chain(xs, gs, False)
+        ops.set_sync_group(keep[0])
+        ops.set_peer_exchange(keep[1])
+        e_out = float((out_dp - out_1p[sl4]).norm() / out_1p[sl4].norm())
+        e_dx = float((dx_dp - dx_1p[sl4]).norm() / dx_1p[sl4].norm())
+        e_g = float((dgam_dp - dgam_1p).norm() / dgam_1p.norm())
+        print(f"isolated SyncBN chain (6 layers): out {e_out:.2e}  dx {e_dx:.2e}  dgamma {e_g:.2e}", flush=True)
+        ok &= e_out < 2e-2 and e_dx < 2e-2 and e_g < 2e-2
+    dist.barrier()
+    tr = build(dev, parallel.GradSync(bucket_bytes=int(os.environ.get("MGC_BUCKET_MB", "1")) << 20))
     sl = slice(rank * per, (rank + 1) * per)
     def flat_grads(t, dp):
         """Flattened gradients the optimizers consumed in the last step (dp: all-reduced bucket views / world);
