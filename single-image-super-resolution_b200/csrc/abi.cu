@@ -15,6 +15,7 @@
 #include "optim.h"
 #include "peer.h"
 #include "spectral.h"
+#include "trunk_fused.h"
 #include "wgrad_tc.h"
 
 using namespace sisr;
@@ -468,6 +469,21 @@ int sisr_mse_fwd(const float* a, const float* b, long long n, float coef, float*
 int sisr_mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
                  float* gb, void* s) {
   return wrap(mse_bwd(a, b, n, coef, gout, ga, gb, S(s)), "mse_bwd");
+}
+
+// ------------------------------------------------------------------ fused persistent trunk forward
+static_assert(sizeof(sisr_trunk_layer) == sizeof(TrunkLayerHost), "sisr_trunk_layer layout");
+int sisr_trunk_supported(int nb, int h, int w, int n_layers) { return trunk_fused_supported(nb, h, w, n_layers) ? 1 : 0; }
+size_t sisr_trunk_workspace_bytes(int n_layers) { return trunk_fused_workspace_bytes(n_layers); }
+int sisr_trunk_forward(const sisr_bf16* x0, int nb, int h, int w, const sisr_bf16* weights, int w_row_stride,
+                       const sisr_trunk_layer* layers, int n_layers, sisr_bf16* y_all, sisr_bf16* a_all,
+                       float momentum, float eps, void* workspace, void* s) {
+  if (!x0 || !weights || !layers || !y_all || !a_all || !workspace) return fail(1, "trunk_forward: null argument");
+  if (int rc = trunk_fused_forward(B(x0), nb, h, w, B(weights), w_row_stride,
+                                   reinterpret_cast<const TrunkLayerHost*>(layers), n_layers, B(y_all), B(a_all),
+                                   momentum, eps, workspace, S(s)))
+    return fail(rc, "trunk_forward: %s", trunk_fused_last_error());
+  return 0;
 }
 
 // ------------------------------------------------------------------ image-quality metrics

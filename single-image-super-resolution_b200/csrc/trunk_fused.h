@@ -19,7 +19,7 @@ struct TrunkLayerHost {
   long long* nbt;
   const float* slope;
   float* aux;
-  int residual_layer;
+  int residual_layer, reserved;
 };
 
 struct TrunkLayerDev {
