@@ -84,13 +84,13 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   uint8_t* smem_w = smem;
   uint8_t* smem_box = smem + kGroups * kWTile;
   float* xbuf = reinterpret_cast<float*>(smem_box + p.box_alloc);
-  uint32_t* ytile = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(xbuf) + kXBytes);   // [n_total][kYPitch]
+  uint32_t* ytile = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(xbuf) + kXBytes);   // [y_rows][kYPitch]
   __shared__ __align__(8) uint64_t w_bar;
   __shared__ __align__(8) uint64_t box_full;
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_sum[2 * 64];
-  __shared__ float s_part[2][128];
+  __shared__ __align__(16) float s_red10[10][128];
   __shared__ float s_scale[64], s_shift[64];
 
   const int warp = threadIdx.x >> 5;
@@ -265,17 +265,37 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 
     // ------------------------------------------------------------------ statistics -> scale / shift
     if (warp == 0 && lane == 0 && l + 1 < p.n_layers) load_weights(l + 1);    // lands during pass B
-    if (threadIdx.x < 256) {
-      const int col = threadIdx.x & 127, rl = threadIdx.x >> 7;
-      const float* src = p.partials + static_cast<size_t>(l) * gridDim.x * 128 + col;
-      float acc = 0.f;
-      for (int r = rl; r < static_cast<int>(gridDim.x); r += 2) acc += __ldcg(src + static_cast<size_t>(r) * 128);
-      s_part[rl][col] = acc;
+    {
+      // partial rows [grid][128]: warp w adds rows w, w + 10, ... (one coalesced 512-byte row per warp load, up to
+      // 16 independent loads in flight per thread), then the ten warp sums are added in a fixed order - the
+      // same bits on every CTA
+      const float4* src = reinterpret_cast<const float4*>(p.partials + static_cast<size_t>(l) * gridDim.x * 128) + lane;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int nrows = static_cast<int>(gridDim.x);
+#pragma unroll 1
+      for (int r0 = warp; r0 < nrows; r0 += 10 * 16) {
+        float4 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int r = r0 + u * 10;
+          v[u] = r < nrows ? __ldcg(src + static_cast<size_t>(r) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        }
+      }
+      reinterpret_cast<float4*>(&s_red10[warp][0])[lane] = acc;
     }
     __syncthreads();
     if (threadIdx.x < 64) {
       const int c = threadIdx.x;
-      const float sum = s_part[0][c] + s_part[1][c], sq = s_part[0][64 + c] + s_part[1][64 + c];
+      float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int w10 = 0; w10 < 10; ++w10) {
+        sum += s_red10[w10][c];
+        sq += s_red10[w10][64 + c];
+      }
       const float mean = sum / p.count;
       const float var = fmaxf(sq / p.count - mean * mean, 0.f);
       const float invstd = rsqrtf(var + p.eps);
@@ -300,34 +320,48 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     {
       const float slope = L.slope ? __ldg(L.slope) : 1.f;
       const __nv_bfloat16* res = L.residual;
-      for (int item = threadIdx.x; item < p.n_valid * 8; item += kThreads) {
-        const int o = item >> 3, seg = item & 7;
-        const int r = o / p.PW, c = o - r * p.PW;
-        if (!(c < p.W && h0 + r < p.H)) continue;
-        const size_t pix = static_cast<size_t>(n_img * p.H + h0 + r) * p.W + c;
-        uint4 val = *reinterpret_cast<const uint4*>(ytile + o * kYPitch + seg * 4);
-        uint4 rv = make_uint4(0, 0, 0, 0);
-        if (res) rv = *reinterpret_cast<const uint4*>(res + pix * 64 + seg * 8);
-        __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
-        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+      const int n_items = p.n_valid * 8;
+#pragma unroll 1
+      for (int item0 = threadIdx.x; item0 < n_items; item0 += 4 * kThreads) {
+        long long pixk[4];
+        uint4 rvk[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int ch = seg * 8 + 2 * j;
-          float2 f = __bfloat1622float2(vh[j]);
-          f.x = fmaf(f.x, s_scale[ch], s_shift[ch]);
-          f.y = fmaf(f.y, s_scale[ch + 1], s_shift[ch + 1]);
-          if (L.slope) {
-            f.x = f.x > 0.f ? f.x : f.x * slope;
-            f.y = f.y > 0.f ? f.y : f.y * slope;
-          }
-          if (res) {
-            const float2 rr = __bfloat1622float2(rh[j]);
-            f.x += rr.x;
-            f.y += rr.y;
-          }
-          vh[j] = __floats2bfloat162_rn(f.x, f.y);
+        for (int k = 0; k < 4; ++k) {
+          const int item = item0 + k * kThreads;
+          const int o = item >> 3, seg = item & 7;
+          const int r = o / p.PW, c = o - r * p.PW;
+          const bool ok = item < n_items && c < p.W && h0 + r < p.H;
+          pixk[k] = ok ? static_cast<long long>(n_img * p.H + h0 + r) * p.W + c : -1;
+          rvk[k] = make_uint4(0, 0, 0, 0);
+          if (ok && res) rvk[k] = *reinterpret_cast<const uint4*>(res + pixk[k] * 64 + seg * 8);
         }
-        *reinterpret_cast<uint4*>(a_out + pix * 64 + seg * 8) = val;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (pixk[k] < 0) continue;
+          const int item = item0 + k * kThreads;
+          const int o = item >> 3, seg = item & 7;
+          uint4 val = *reinterpret_cast<const uint4*>(ytile + o * kYPitch + seg * 4);
+          __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
+          const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rvk[k]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = seg * 8 + 2 * j;
+            float2 f = __bfloat1622float2(vh[j]);
+            f.x = fmaf(f.x, s_scale[ch], s_shift[ch]);
+            f.y = fmaf(f.y, s_scale[ch + 1], s_shift[ch + 1]);
+            if (L.slope) {
+              f.x = f.x > 0.f ? f.x : f.x * slope;
+              f.y = f.y > 0.f ? f.y : f.y * slope;
+            }
+            if (res) {
+              const float2 rr = __bfloat1622float2(rh[j]);
+              f.x += rr.x;
+              f.y += rr.y;
+            }
+            vh[j] = __floats2bfloat162_rn(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(a_out + pixk[k] * 64 + seg * 8) = val;
+        }
       }
     }
     grid_barrier(p.barrier, ++barriers_done * gridDim.x);
@@ -373,7 +407,8 @@ bool make_plan(int nb, int h, int w, Plan& best) {
     const int tiles_h = (h + R - 1) / R;
     const long long tiles = static_cast<long long>(nb) * tiles_h;
     if (tiles > sms()) continue;                        // every tile needs its own co-resident CTA
-    const int smem = kGroups * kWTile + box_alloc + kXBytes + n_total * kYPitch * 4 + 1024;
+    const int y_rows = (R * PW + 31) / 32 * 32;          // the epilogue writes whole 32-position chunks
+    const int smem = kGroups * kWTile + box_alloc + kXBytes + y_rows * kYPitch * 4 + 1024;
     if (smem > 225 * 1024) continue;
     const double mma = 4.0 * kGroups * chunks * (chunk_n * 0.5 + 38.0 > 94.0 ? chunk_n * 0.5 + 38.0 : 94.0);
     const double cost = (mma + 14.0 * n_total + 1500.0) * (1.0 + 0.02 * (tiles_h * R - h));
