@@ -53,22 +53,32 @@ struct TrunkParams {
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// All CTAs are co-resident (cooperative launch).  `target` = arrivals expected so far.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+// All CTAs are co-resident (cooperative launch).  Barrier number k (1, 2, ...): every CTA adds 1 to `count`; the
+// CTA whose addition completes k * grid arrivals publishes k in `flag` (a different 128-byte line), which the
+// others poll with a short sleep - the pollers never touch the line the atomics go to (with all CTAs spinning
+// on the arrival counter itself a barrier cost ~5 us: 128 pollers and 128 atomics on one L2 line).
+__device__ __forceinline__ void grid_barrier(unsigned int* count, unsigned int k) {
   fence_proxy_async_all();           // this thread's global stores -> later TMA (async proxy) reads elsewhere
   __syncthreads();
   if (threadIdx.x == 0) {
+    unsigned int* flag = count + 32;
     __threadfence();
-    atomicAdd(counter, 1u);
-    const long long t0 = clock64();
-    unsigned int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-      if (clock64() - t0 > 4000000000LL) {
-        printf("sisr: trunk grid barrier timeout (block %d, target %u, seen %u)\n", blockIdx.x, target, seen);
-        __trap();
+    const unsigned int old = atomicAdd(count, 1u);
+    if (old + 1 == k * gridDim.x) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(k) : "memory");
+    } else {
+      const long long t0 = clock64();
+      unsigned int seen;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (seen >= k) break;
+        __nanosleep(20);
+        if (clock64() - t0 > 4000000000LL) {
+          printf("sisr: trunk grid barrier timeout (block %d, barrier %u, flag %u)\n", blockIdx.x, k, seen);
+          __trap();
+        }
       }
-    } while (seen < target);
+    }
     __threadfence();
     fence_proxy_async_all();
   }
@@ -261,7 +271,7 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
       }
     }
-    grid_barrier(p.barrier, ++barriers_done * gridDim.x);
+    grid_barrier(p.barrier, ++barriers_done);
 
     // ------------------------------------------------------------------ statistics -> scale / shift
     if (warp == 0 && lane == 0 && l + 1 < p.n_layers) load_weights(l + 1);    // lands during pass B
@@ -364,7 +374,7 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
       }
     }
-    grid_barrier(p.barrier, ++barriers_done * gridDim.x);
+    grid_barrier(p.barrier, ++barriers_done);
   }
 
   tc_fence_before();
