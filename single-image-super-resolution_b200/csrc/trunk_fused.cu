@@ -48,6 +48,7 @@ struct TrunkParams {
   __nv_bfloat16* a_all;            // [n_layers][NB, H, W, 64]: layer outputs
   float* partials;                 // [n_layers][grid][128]
   unsigned int* barrier;           // zeroed before the launch
+  long long* timing;               // debug (SISR_TRUNK_TIMING=1): [n_layers][8] clock64 stamps of CTA 0, else null
   TrunkLayerDev layer[kTrunkMaxLayers];
 };
 
@@ -201,6 +202,8 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
       float s1 = 0.f, s2 = 0.f;
       int ready = 0;
+      const bool stamp = p.timing && blockIdx.x == 0 && threadIdx.x == 64;
+      if (stamp) p.timing[l * 8 + 0] = clock64();
       if (threadIdx.x - 64 < 128) s_sum[threadIdx.x - 64] = 0.f;
       asm volatile("bar.sync 3, 256;" ::: "memory");
 #pragma unroll 1
@@ -213,6 +216,7 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           ++ready;
         }
         tc_fence_after();
+        if (stamp && pc == half) p.timing[l * 8 + 1] = clock64();       // first instruction chunk complete
         uint32_t raw[32];
         tmem_ld_32x32(trow + o0 + (is_lo ? 0 : 1), raw);
         const int o = o0 + lane;
@@ -259,6 +263,7 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         atomicAdd(&s_sum[64 + co], s2);
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");       // y tile and the CTA's sums are complete
+      if (stamp) p.timing[l * 8 + 2] = clock64();
       const int et = threadIdx.x - 64;                      // 0..255
       if (et < 128) p.partials[(static_cast<size_t>(l) * gridDim.x + blockIdx.x) * 128 + et] = s_sum[et];
       // y -> global (16 bytes per thread and step)
@@ -271,7 +276,10 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
       }
     }
+    const bool stamp2 = p.timing && blockIdx.x == 0 && threadIdx.x == 64;
+    if (stamp2) p.timing[l * 8 + 3] = clock64();
     grid_barrier(p.barrier, ++barriers_done);
+    if (stamp2) p.timing[l * 8 + 4] = clock64();
 
     // ------------------------------------------------------------------ statistics -> scale / shift
     if (warp == 0 && lane == 0 && l + 1 < p.n_layers) load_weights(l + 1);    // lands during pass B
@@ -326,6 +334,7 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     }
     __syncthreads();
 
+    if (stamp2) p.timing[l * 8 + 5] = clock64();
     // ------------------------------------------------------------------ pass B: normalise (+PReLU / +residual)
     {
       const float slope = L.slope ? __ldg(L.slope) : 1.f;
@@ -374,7 +383,9 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
       }
     }
+    if (stamp2) p.timing[l * 8 + 6] = clock64();
     grid_barrier(p.barrier, ++barriers_done);
+    if (stamp2) p.timing[l * 8 + 7] = clock64();
   }
 
   tc_fence_before();
@@ -499,12 +510,39 @@ int trunk_fused_forward(const __nv_bfloat16* x0, int nb, int h, int w, const __n
     configured = pl.smem;
   }
   cudaMemsetAsync(workspace, 0, 256, stream);
+  static const bool want_timing = getenv("SISR_TRUNK_TIMING") != nullptr;      // debug: phase breakdown of CTA 0
+  static long long* d_timing = nullptr;
+  if (want_timing && !d_timing) cudaMalloc(&d_timing, sizeof(long long) * kTrunkMaxLayers * 8);
+  p.timing = want_timing ? d_timing : nullptr;
   void* args[] = {&tw, &tx0, &ta, &p};
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(trunk_fwd_kernel), dim3(pl.tiles),
                                               dim3(kThreads), args, pl.smem, stream);
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "trunk_fused launch: %s", cudaGetErrorString(e));
     return 4;
+  }
+  if (want_timing) {
+    static int printed = 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    if (cap == cudaStreamCaptureStatusNone && printed < 2 && cudaStreamSynchronize(stream) == cudaSuccess) {
+      ++printed;
+      long long h[kTrunkMaxLayers * 8];
+      cudaMemcpy(h, d_timing, sizeof(long long) * n_layers * 8, cudaMemcpyDeviceToHost);
+      double acc[8] = {};
+      for (int l = 1; l < n_layers; ++l) {
+        acc[0] += h[l * 8 + 0] - h[(l - 1) * 8 + 7];      // after barrier 2 -> epilogue warps enter
+        for (int i = 1; i < 8; ++i) acc[i] += h[l * 8 + i] - h[l * 8 + i - 1];
+      }
+      const char* names[8] = {"layer entry", "box load + first MMA chunk", "epilogue A (+ second chunk)",
+                              "partials + y store", "grid barrier 1", "statistics", "pass B", "grid barrier 2"};
+      double tot = 0;
+      for (int i = 0; i < 8; ++i) tot += acc[i];
+      printf("trunk_fused phase breakdown (CTA 0, cycles per layer, %d layers):\n", n_layers - 1);
+      for (int i = 0; i < 8; ++i) printf("  %-30s %8.0f\n", names[i], acc[i] / (n_layers - 1));
+      printf("  %-30s %8.0f\n", "total", tot / (n_layers - 1));
+      fflush(stdout);
+    }
   }
   return 0;
 }
