@@ -86,6 +86,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* count, unsigned int k
   __syncthreads();
 }
 
+constexpr int kMaxItems = 8;      // 16-byte items of pass B per thread: n_valid * 8 <= kMaxItems * kThreads
+constexpr int kMaxChunks = 5;     // 32-position chunks per epilogue half: n_valid <= 320
+
 __global__ void __launch_bounds__(kThreads, 1)
 trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x0,
                  const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TrunkParams p) {
@@ -94,14 +97,14 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_w = smem;
   uint8_t* smem_box = smem + kGroups * kWTile;
-  float* xbuf = reinterpret_cast<float*>(smem_box + p.box_alloc);
-  uint32_t* ytile = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(xbuf) + kXBytes);   // [y_rows][kYPitch]
+  float* xbuf = reinterpret_cast<float*>(smem_box + p.box_alloc);          // [half][parity][64][kXRow]
+  float* s_red10 = xbuf;                                                   // [10][128], statistics phase only
+  uint32_t* ytile = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(xbuf) + 2 * kXBytes);   // [y_rows][kYPitch]
   __shared__ __align__(8) uint64_t w_bar;
   __shared__ __align__(8) uint64_t box_full;
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_sum[2 * 64];
-  __shared__ __align__(16) float s_red10[10][128];
   __shared__ float s_scale[64], s_shift[64];
 
   const int warp = threadIdx.x >> 5;
@@ -135,7 +138,7 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  // weights of layer l: rows [128 l, 128 l + 64) of the prepared-weight matrix, tap t at columns 64 t
+  // weights of layer l: rows [l * w_row_stride, + 64) of the prepared-weight matrix, tap t at columns 64 t
   auto load_weights = [&](int l) {
     const uint32_t wb = smem_u32(&w_bar);
     mbar_expect_tx(wb, 9 * (kWTile / 2));
@@ -149,12 +152,52 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   };
   if (warp == 0 && lane == 0) load_weights(0);
 
+  // ---- layer-invariant geometry: the tile, its positions and this thread's share of them are the same in
+  // every layer, so the index arithmetic (divisions by the box pitch) is done once
+  // pass B items: item = threadIdx.x + k * kThreads -> (position o, 16-byte segment); pix < 0: not a pixel
+  int b_pix[kMaxItems], b_src[kMaxItems];
+#pragma unroll
+  for (int k = 0; k < kMaxItems; ++k) {
+    const int item = threadIdx.x + k * kThreads;
+    const int o = item >> 3, seg = item & 7;
+    const int r = o / p.PW, c = o - r * p.PW;
+    const bool ok = item < p.n_valid * 8 && c < p.W && h0 + r < p.H;
+    b_pix[k] = ok ? ((n_img * p.H + h0 + r) * p.W + c) * 8 + seg : -1;      // in 16-byte units of a [.., 64] tensor
+    b_src[k] = o * kYPitch + seg * 4;
+  }
+  // epilogue A: validity of the 32 positions of each chunk of this warp's half
+  const int quad = warp & 3;
+  const int half = warp >= 2 ? (warp - 2) >> 2 : 0;
+  const bool is_lo = quad < 2;
+  const int co = (quad & 1) * 32 + lane;
+  const int n_pchunks = (p.n_valid + 31) >> 5;
+  uint32_t vm[kMaxChunks];
+#pragma unroll
+  for (int j = 0; j < kMaxChunks; ++j) {
+    const int o = (half + 2 * j) * 32 + lane;
+    const int r = o / p.PW, c = o - r * p.PW;
+    vm[j] = __ballot_sync(0xffffffffu, o < p.n_valid && c < p.W && h0 + r < p.H);
+  }
+  float bias_next = (warp >= 2 && p.layer[0].bias) ? p.layer[0].bias[co] : 0.f;
+
   unsigned int barriers_done = 0;
   for (int l = 0; l < p.n_layers; ++l) {
     const TrunkLayerDev& L = p.layer[l];
     const uint32_t parity = l & 1;
     __nv_bfloat16* const y_out = p.y_all + static_cast<size_t>(l) * p.layer_elems;
     __nv_bfloat16* const a_out = p.a_all + static_cast<size_t>(l) * p.layer_elems;
+    // per-channel BN parameters and the activation slope: requested now, used after barrier 1
+    float bn_g = 0.f, bn_b = 0.f, bn_rm = 0.f, bn_rv = 0.f;
+    if (threadIdx.x < 64) {
+      bn_g = L.gamma[threadIdx.x];
+      bn_b = L.beta[threadIdx.x];
+      if (blockIdx.x == 0) {
+        bn_rm = L.running_mean[threadIdx.x];
+        bn_rv = L.running_var[threadIdx.x];
+      }
+    }
+    const float slope = L.slope ? __ldg(L.slope) : 1.f;
+    const bool stamp2 = p.timing && blockIdx.x == 0 && threadIdx.x == 64;
     // ------------------------------------------------------------------ conv
     if (warp == 0) {
       if (lane == 0) {
@@ -191,24 +234,22 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       __syncwarp();
     } else {
       // -------------------------------------------------------------- epilogue A
-      const int quad = warp & 3;
-      const int half = (warp - 2) >> 2;
-      const bool is_lo = quad < 2;
-      const int co = (quad & 1) * 32 + lane;
-      const float bias = L.bias ? L.bias[co] : 0.f;
-      float* xb = xbuf + half * 64 * kXRow;
-      const int n_pchunks = (p.n_valid + 31) >> 5;
-      const int bar_full = 4 + half, bar_free = 6 + half;
+      // quads 2,3 (D_hi) hand their values to quads 0,1 (D_lo) through a double-buffered shared-memory tile, so
+      // that they run one chunk ahead; bias, bf16 rounding, channel sums and the y tile are the lo warps' work
+      const float bias = bias_next;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
       float s1 = 0.f, s2 = 0.f;
       int ready = 0;
       const bool stamp = p.timing && blockIdx.x == 0 && threadIdx.x == 64;
       if (stamp) p.timing[l * 8 + 0] = clock64();
       if (threadIdx.x - 64 < 128) s_sum[threadIdx.x - 64] = 0.f;
-      asm volatile("bar.sync 3, 256;" ::: "memory");
+      int j = 0;
 #pragma unroll 1
-      for (int pc = half; pc < n_pchunks; pc += 2) {
+      for (int pc = half; pc < n_pchunks; pc += 2, ++j) {
         const int o0 = pc * 32;
+        const int par = j & 1;
+        float* xb = xbuf + ((half * 2 + par) * 64) * kXRow;
+        const int bar_full = 4 + half * 2 + par, bar_free = 8 + half * 2 + par;
         int need = (o0 + 32) / p.chunk_n + 1;
         if (need > p.chunks) need = p.chunks;
         while (ready < need) {
@@ -216,20 +257,17 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           ++ready;
         }
         tc_fence_after();
-        if (stamp && pc == half) p.timing[l * 8 + 1] = clock64();       // first instruction chunk complete
+        if (stamp && j == 0) p.timing[l * 8 + 1] = clock64();       // first instruction chunk complete
         uint32_t raw[32];
         tmem_ld_32x32(trow + o0 + (is_lo ? 0 : 1), raw);
-        const int o = o0 + lane;
-        const int r = o / p.PW, c = o - r * p.PW;
-        const bool ok = o < p.n_valid && c < p.W && h0 + r < p.H;
-        const uint32_t vmask = __ballot_sync(0xffffffffu, ok);
         tmem_ld_wait();
         if (!is_lo) {
+          if (j >= 2) asm volatile("bar.sync %0, 128;" ::"r"(bar_free) : "memory");   // chunk j-2 has been read
 #pragma unroll
           for (int i = 0; i < 32; ++i) xb[co * kXRow + i] = __uint_as_float(raw[i]);
           asm volatile("bar.arrive %0, 128;" ::"r"(bar_full) : "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_free) : "memory");
         } else {
+          const uint32_t vmask = vm[j < kMaxChunks ? j : kMaxChunks - 1];
           asm volatile("bar.sync %0, 128;" ::"r"(bar_full) : "memory");
           float v[32];
 #pragma unroll
@@ -253,6 +291,11 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           }
         }
       }
+      if (!is_lo) {
+        // consume the "read" arrivals of the last two chunks, so that every named barrier ends the layer balanced
+        if (j >= 2) asm volatile("bar.sync %0, 128;" ::"r"(8 + half * 2 + (j & 1)) : "memory");
+        if (j >= 1) asm volatile("bar.sync %0, 128;" ::"r"(8 + half * 2 + ((j - 1) & 1)) : "memory");
+      }
       while (ready < p.chunks) {
         mbar_wait(smem_u32(&tmem_full_bar[ready]), parity);
         ++ready;
@@ -266,23 +309,21 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       if (stamp) p.timing[l * 8 + 2] = clock64();
       const int et = threadIdx.x - 64;                      // 0..255
       if (et < 128) p.partials[(static_cast<size_t>(l) * gridDim.x + blockIdx.x) * 128 + et] = s_sum[et];
-      // y -> global (16 bytes per thread and step)
-      for (int item = et; item < p.n_valid * 8; item += 256) {
-        const int o = item >> 3, seg = item & 7;
-        const int r = o / p.PW, c = o - r * p.PW;
-        if (c < p.W && h0 + r < p.H) {
-          const size_t pix = static_cast<size_t>(n_img * p.H + h0 + r) * p.W + c;
-          *reinterpret_cast<uint4*>(y_out + pix * 64 + seg * 8) = *reinterpret_cast<const uint4*>(ytile + o * kYPitch + seg * 4);
-        }
-      }
+      if (l + 1 < p.n_layers) bias_next = p.layer[l + 1].bias ? p.layer[l + 1].bias[co] : 0.f;
     }
-    const bool stamp2 = p.timing && blockIdx.x == 0 && threadIdx.x == 64;
     if (stamp2) p.timing[l * 8 + 3] = clock64();
     grid_barrier(p.barrier, ++barriers_done);
     if (stamp2) p.timing[l * 8 + 4] = clock64();
 
     // ------------------------------------------------------------------ statistics -> scale / shift
-    if (warp == 0 && lane == 0 && l + 1 < p.n_layers) load_weights(l + 1);    // lands during pass B
+    // residual rows of pass B: requested now, consumed after the statistics
+    const uint4* res4 = reinterpret_cast<const uint4*>(L.residual);
+    uint4 rvk[kMaxItems];
+#pragma unroll
+    for (int k = 0; k < kMaxItems; ++k) {
+      rvk[k] = make_uint4(0, 0, 0, 0);
+      if (res4 && b_pix[k] >= 0) rvk[k] = res4[b_pix[k]];
+    }
     {
       // partial rows [grid][128]: warp w adds rows w, w + 10, ... (one coalesced 512-byte row per warp load, up to
       // 16 independent loads in flight per thread), then the ten warp sums are added in a fixed order - the
@@ -303,7 +344,7 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
         }
       }
-      reinterpret_cast<float4*>(&s_red10[warp][0])[lane] = acc;
+      reinterpret_cast<float4*>(s_red10 + warp * 128)[lane] = acc;
     }
     __syncthreads();
     if (threadIdx.x < 64) {
@@ -311,14 +352,14 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       float sum = 0.f, sq = 0.f;
 #pragma unroll
       for (int w10 = 0; w10 < 10; ++w10) {
-        sum += s_red10[w10][c];
-        sq += s_red10[w10][64 + c];
+        sum += s_red10[w10 * 128 + c];
+        sq += s_red10[w10 * 128 + 64 + c];
       }
       const float mean = sum / p.count;
       const float var = fmaxf(sq / p.count - mean * mean, 0.f);
       const float invstd = rsqrtf(var + p.eps);
-      const float sc = L.gamma[c] * invstd;
-      const float sh = L.beta[c] - mean * sc;
+      const float sc = bn_g * invstd;
+      const float sh = bn_b - mean * sc;
       s_scale[c] = sc;
       s_shift[c] = sh;
       if (blockIdx.x == 0) {
@@ -327,60 +368,45 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         L.aux[128 + c] = mean;
         L.aux[192 + c] = invstd;
         const float unbiased = p.count > 1.f ? var * p.count / (p.count - 1.f) : var;
-        L.running_mean[c] = (1.f - p.momentum) * L.running_mean[c] + p.momentum * mean;
-        L.running_var[c] = (1.f - p.momentum) * L.running_var[c] + p.momentum * unbiased;
+        L.running_mean[c] = (1.f - p.momentum) * bn_rm + p.momentum * mean;
+        L.running_var[c] = (1.f - p.momentum) * bn_rv + p.momentum * unbiased;
         if (c == 0 && L.nbt) *L.nbt += 1;
       }
     }
     __syncthreads();
+    if (warp == 0 && lane == 0 && l + 1 < p.n_layers) load_weights(l + 1);    // lands during pass B / barrier 2
 
     if (stamp2) p.timing[l * 8 + 5] = clock64();
-    // ------------------------------------------------------------------ pass B: normalise (+PReLU / +residual)
+    // ------------------------------------------------------------------ pass B: y -> global; normalise (+PReLU / +residual)
     {
-      const float slope = L.slope ? __ldg(L.slope) : 1.f;
-      const __nv_bfloat16* res = L.residual;
-      const int n_items = p.n_valid * 8;
-#pragma unroll 1
-      for (int item0 = threadIdx.x; item0 < n_items; item0 += 4 * kThreads) {
-        long long pixk[4];
-        uint4 rvk[4];
+      uint4* const y4 = reinterpret_cast<uint4*>(y_out);
+      uint4* const a4 = reinterpret_cast<uint4*>(a_out);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int item = item0 + k * kThreads;
-          const int o = item >> 3, seg = item & 7;
-          const int r = o / p.PW, c = o - r * p.PW;
-          const bool ok = item < n_items && c < p.W && h0 + r < p.H;
-          pixk[k] = ok ? static_cast<long long>(n_img * p.H + h0 + r) * p.W + c : -1;
-          rvk[k] = make_uint4(0, 0, 0, 0);
-          if (ok && res) rvk[k] = *reinterpret_cast<const uint4*>(res + pixk[k] * 64 + seg * 8);
-        }
+      for (int k = 0; k < kMaxItems; ++k) {
+        if (b_pix[k] < 0) continue;
+        uint4 val = *reinterpret_cast<const uint4*>(ytile + b_src[k]);
+        y4[b_pix[k]] = val;                              // the conv output, kept for the backward pass
+        const int seg = (threadIdx.x + k * kThreads) & 7;
+        __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
+        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rvk[k]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (pixk[k] < 0) continue;
-          const int item = item0 + k * kThreads;
-          const int o = item >> 3, seg = item & 7;
-          uint4 val = *reinterpret_cast<const uint4*>(ytile + o * kYPitch + seg * 4);
-          __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
-          const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rvk[k]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = seg * 8 + 2 * j;
-            float2 f = __bfloat1622float2(vh[j]);
-            f.x = fmaf(f.x, s_scale[ch], s_shift[ch]);
-            f.y = fmaf(f.y, s_scale[ch + 1], s_shift[ch + 1]);
-            if (L.slope) {
-              f.x = f.x > 0.f ? f.x : f.x * slope;
-              f.y = f.y > 0.f ? f.y : f.y * slope;
-            }
-            if (res) {
-              const float2 rr = __bfloat1622float2(rh[j]);
-              f.x += rr.x;
-              f.y += rr.y;
-            }
-            vh[j] = __floats2bfloat162_rn(f.x, f.y);
+        for (int jj = 0; jj < 4; ++jj) {
+          const int ch = seg * 8 + 2 * jj;
+          float2 f = __bfloat1622float2(vh[jj]);
+          f.x = fmaf(f.x, s_scale[ch], s_shift[ch]);
+          f.y = fmaf(f.y, s_scale[ch + 1], s_shift[ch + 1]);
+          if (L.slope) {
+            f.x = f.x > 0.f ? f.x : f.x * slope;
+            f.y = f.y > 0.f ? f.y : f.y * slope;
           }
-          *reinterpret_cast<uint4*>(a_out + pixk[k] * 64 + seg * 8) = val;
+          if (res4) {
+            const float2 rr = __bfloat1622float2(rh[jj]);
+            f.x += rr.x;
+            f.y += rr.y;
+          }
+          vh[jj] = __floats2bfloat162_rn(f.x, f.y);
         }
+        a4[b_pix[k]] = val;
       }
     }
     if (stamp2) p.timing[l * 8 + 6] = clock64();
@@ -421,7 +447,7 @@ bool make_plan(int nb, int h, int w, Plan& best) {
       n_total = (R * PW + 31) / 32 * 32;
       chunks = 2;
     }
-    if (n_total > 512) break;
+    if (n_total > 512 || R * PW > 32 * 2 * kMaxChunks || R * PW * 8 > kMaxItems * kThreads) break;
     const int chunk_n = n_total / chunks;
     const int rows_needed = n_total + 2 * PW + 2 > (R + 2) * PW ? n_total + 2 * PW + 2 : (R + 2) * PW;
     const int box_alloc = (rows_needed * 128 + 1023) / 1024 * 1024;
@@ -429,7 +455,7 @@ bool make_plan(int nb, int h, int w, Plan& best) {
     const long long tiles = static_cast<long long>(nb) * tiles_h;
     if (tiles > sms()) continue;                        // every tile needs its own co-resident CTA
     const int y_rows = (R * PW + 31) / 32 * 32;          // the epilogue writes whole 32-position chunks
-    const int smem = kGroups * kWTile + box_alloc + kXBytes + y_rows * kYPitch * 4 + 1024;
+    const int smem = kGroups * kWTile + box_alloc + 2 * kXBytes + y_rows * kYPitch * 4 + 1024;
     if (smem > 225 * 1024) continue;
     const double mma = 4.0 * kGroups * chunks * (chunk_n * 0.5 + 38.0 > 94.0 ? chunk_n * 0.5 + 38.0 : 94.0);
     const double cost = (mma + 14.0 * n_total + 1500.0) * (1.0 + 0.02 * (tiles_h * R - h));
