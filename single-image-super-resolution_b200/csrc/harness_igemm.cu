@@ -320,11 +320,15 @@ int main(int argc, char** argv) {
       {"c256_512_6x6_n8", 8, 6, 6, 256, 512, 1, 0, ACT_RELU, 0},
       {"c128_256_s2_12x12_n8", 8, 12, 12, 128, 256, 2, 0, ACT_NONE, 1},
   };
-  if (argc > 1 && argv[1][0] == 't') {
-    // transposed halo-fed kernel with stacked taps (igemm_th.cu), 64 -> 64 channels: "harness_igemm th"
+  if (argc > 1 && (argv[1][0] == 't' || argv[1][0] == 'p')) {
+    // halo-fed kernels for the 64 -> 64 channel layers: "harness_igemm th" = weights on M with stacked taps
+    // (igemm_th.cu), "harness_igemm pm [grp]" = pixels on M (igemm_pm.cu)
+    const bool pm = argv[1][0] == 'p';
     igemm_set_transposed(1);
     igemm_set_th(1);
-    printf("-- transposed halo kernel, stacked taps (64 -> 64)\n");
+    igemm_set_pm(pm ? 1 : 0);
+    if (pm && argc > 2) igemm_set_pm_grp(atoi(argv[2]));
+    printf("-- halo-fed kernel, %s (64 -> 64)\n", pm ? "pixels on M" : "weights on M, stacked taps");
     const ConvCase th_cases[] = {
         {"t_c64_24x24_n4", 4, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
         {"t_c64_12x12_n3", 3, 12, 12, 64, 64, 1, 0, ACT_PRELU, 1},
@@ -337,8 +341,8 @@ int main(int argc, char** argv) {
     for (const auto& cc : th_cases) {
       IgemmProblem q;
       fill_fprop_problem(q, cc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-      if (!igemm_th_supported(q)) {
-        printf("[conv %s] NOT routed to the th kernel\n", cc.name);
+      if (pm ? !igemm_pm_supported(q) : !igemm_th_supported(q)) {
+        printf("[conv %s] NOT routed to the halo-fed kernel\n", cc.name);
         ++fails;
       }
       fails += run_conv(cc, false);
@@ -348,12 +352,18 @@ int main(int argc, char** argv) {
         {"vgg_c64_96x96_n64", 64, 96, 96, 64, 64, 1, 0, ACT_RELU, 0},
     };
     for (const auto& cc : th_big) fails += run_conv(cc, true);
+    if (pm) {
+      igemm_set_pm(0);
+      for (const auto& cc : th_big) fails += run_conv(cc, true);    // same shapes on igemm_th
+    }
     igemm_set_th(0);
+    igemm_set_pm(0);
     for (const auto& cc : th_big) fails += run_conv(cc, true);      // same shapes on the im2col-fed transposed kernel
     printf("harness: %d failure(s)\n", fails);
     return fails ? 1 : 0;
   }
   igemm_set_th(0);
+  igemm_set_pm(0);
   igemm_set_transposed(1);
   printf("-- default engine (transposed tiles for Cout <= 128)\n");
   for (const auto& cc : convs) fails += run_conv(cc, false);

@@ -69,6 +69,13 @@ bool igemm_th_supported(const IgemmProblem& p);
 int igemm_th_launch(const IgemmProblem& p, cudaStream_t stream);
 void igemm_set_th(int on);             // 0: never use it (A-B timing, SISR_TH=0)
 const char* igemm_th_last_error();
+// Halo-fed kernel with the pixels on the UMMA M side (igemm_pm.cu): the same problems as igemm_th; igemm_launch()
+// tries it before igemm_th.
+bool igemm_pm_supported(const IgemmProblem& p);
+int igemm_pm_launch(const IgemmProblem& p, cudaStream_t stream);
+void igemm_set_pm(int on);             // 0: never use it (A-B timing, SISR_PM=0)
+void igemm_set_pm_grp(int grp);        // M tiles whose instructions are interleaved (0: planner's choice)
+const char* igemm_pm_last_error();
 int igemm_max_ctas();   // the persistent grid never exceeds this (number of SMs)
 const char* igemm_last_error();
 

@@ -735,6 +735,11 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
              p.Cout, p.num_taps, p.ldc);
     return 1;
   }
+  if (igemm_pm_supported(p)) {
+    const int rc = igemm_pm_launch(p, stream);
+    if (rc) snprintf(g_err, sizeof g_err, "%s", igemm_pm_last_error());
+    return rc;
+  }
   if (igemm_th_supported(p)) {
     const int rc = igemm_th_launch(p, stream);
     if (rc) snprintf(g_err, sizeof g_err, "%s", igemm_th_last_error());

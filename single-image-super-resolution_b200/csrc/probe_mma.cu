@@ -111,7 +111,7 @@ constexpr int kReps = 512;
 
 // mode 0: SS, 1: TS.  One CTA, 128 threads.  A tile: 128 rows x 64 k (16 KB), B tile: N rows x 64 k.
 __global__ void __launch_bounds__(128)
-probe_1cta(int M, int N, int mode, long long* cycles) {
+probe_1cta(int M, int N, int mode, long long* cycles, int nacc = 1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -140,10 +140,12 @@ probe_1cta(int M, int N, int mode, long long* cycles) {
     for (int r = 0; r < kReps; ++r) {
       const int k = r & 3;
       const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+      // nacc > 1: consecutive instructions go to different accumulators (is the floor a dependency latency?)
+      const uint32_t d_acc = tmem + (r % nacc) * N;
       if (mode == 0)
-        umma_bf16(tmem, umma_smem_desc(a_addr + k * 32, 16, 1024), db, idesc, r > 0);
+        umma_bf16(d_acc, umma_smem_desc(a_addr + k * 32, 16, 1024), db, idesc, r >= nacc);
       else
-        umma_bf16_ts(tmem, tmem_a + k * 8, db, idesc, r > 0);
+        umma_bf16_ts(d_acc, tmem_a + k * 8, db, idesc, r >= nacc);
     }
     umma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
@@ -160,7 +162,7 @@ probe_1cta(int M, int N, int mode, long long* cycles) {
 
 // CTA pair: M = 256, each CTA holds 128 A rows and N/2 B rows.  Leader issues, both wait.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
-probe_2cta(int N, long long* cycles) {
+probe_2cta(int N, long long* cycles, int nacc = 1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -189,8 +191,8 @@ probe_2cta(int N, long long* cycles) {
     const long long t0 = clock64();
     for (int r = 0; r < kReps; ++r) {
       const int k = r & 3;
-      umma_bf16_pair(tmem, umma_smem_desc(a_addr + k * 32, 16, 1024), umma_smem_desc(b_addr + k * 32, 16, 1024),
-                     idesc, r > 0);
+      umma_bf16_pair(tmem + (r % nacc) * N, umma_smem_desc(a_addr + k * 32, 16, 1024),
+                     umma_smem_desc(b_addr + k * 32, 16, 1024), idesc, r >= nacc);
     }
     umma_commit_pair(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
@@ -233,6 +235,18 @@ int main() {
     for (int rep = 0; rep < 2; ++rep) probe_2cta<<<2, 128, smem>>>(N, d);
     report("2CTA", 256, N);
   }
+  // independent accumulators, round robin (SS form; the TS form keeps its A operand in columns 256..)
+  for (int nacc : {2, 4})
+    for (int N : {64, 128}) {
+      if (nacc * N > 256) continue;
+      for (int rep = 0; rep < 2; ++rep) probe_1cta<<<1, 128, smem>>>(128, N, 0, d, nacc);
+      char what[16];
+      snprintf(what, sizeof what, "SSx%d", nacc);
+      report(what, 128, N);
+      for (int rep = 0; rep < 2; ++rep) probe_2cta<<<2, 128, smem>>>(N, d, nacc);
+      snprintf(what, sizeof what, "2Cx%d", nacc);
+      report(what, 256, N);
+    }
   CK(cudaFree(d));
   return 0;
 }
