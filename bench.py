@@ -488,7 +488,7 @@ def dominant_share():
 
 
 def re_kernel(line):
-    return any(k in line for k in ("igemm_t_kernel", "igemm_th_kernel"))
+    return any(k in line for k in ("igemm_t_kernel", "igemm_th_kernel", "igemm_pm_kernel"))
 
 
 def run_ours(args):
@@ -681,7 +681,7 @@ def run_ours(args):
         hbm = []
     else:
         dom = time_dominant_kernel(dev, batch, frozen=cfg["frozen"])
-        dom["kernel"] = "igemm_t_kernel / igemm_th_kernel: " + dom["kernel"]
+        dom["kernel"] = "igemm_t_kernel / igemm_pm_kernel: " + dom["kernel"]
         others = [time_conv_kernel(dev, batch, 96, 64, 64, False), time_conv_kernel(dev, batch, 48, 128, 128, False),
                   time_conv_kernel(dev, batch, 24, 256, 256, False), time_conv_kernel(dev, batch, 12, 512, 512, False)]
         hbm = time_hbm_kernels(dev, batch)

@@ -45,9 +45,9 @@ int sisr_stats_rows(void);
 /* debug / A-B timing: 0 = layers with cout <= 128 use the 128-pixel x cout tiles instead of the
  * 128-channel x 256-pixel (transposed) tiles */
 int sisr_debug_transposed(int on);
-/* debug / A-B timing: 0 = the 64 -> 64 channel stride-1 layers (generator trunk, model_generator.py:10,13,39)
- * do not use the transposed halo-fed kernel with stacked filter taps (csrc/igemm_th.cu); default 1 */
-int sisr_debug_th_mode(int on);
+/* debug / A-B timing: 0 = the 64 -> 64 channel stride-1 layers (generator trunk, model_generator.py:10,13,39;
+ * VGG conv1_2) do not use the halo-fed kernel with the pixels on the UMMA M side (csrc/igemm_pm.cu); default 1 */
+int sisr_debug_pm_mode(int on);
 /* 1 if the tcgen05 implicit-GEMM engine takes this fprop/dgrad shape, 0 if the CUDA-core kernel does */
 int sisr_conv_uses_tensor_cores(const sisr_conv_desc* d);
 
@@ -97,32 +97,6 @@ int sisr_weight_grad_finish(const float* g_prepared, const float* w_orig, const 
                             const float* sigma, float* dw, const float* dbias_perm, float* dbias,
                             int cout, int cin, int k, int ps_r, int accumulate, float* workspace,
                             void* stream);
-
-/* ---- the generator's residual trunk in ONE persistent cooperative launch (single GPU, train mode):
- *      model_generator.py:5-19 (BasicBlock), 36-41 (block_list / block_list_end), 86-93 (forward_no_end) - every
- *      conv3x3(64 -> 64) + train-mode BatchNorm2d + PReLU / residual add of the trunk, with two grid barriers per
- *      layer (batch statistics; neighbour halo).  Layer l reads the output of layer l - 1 (layer 0 reads x0).
- *      `layers` is a HOST array of device pointers; residual_layer: -1 none, -2 = x0, l' >= 0 = output of layer
- *      l'; slope: PReLU slope or NULL; aux: [4][64] = scale, shift, mean, invstd (saved for the backward pass).
- *      weights: the prepared bf16 matrix of sisr_weight_prep_batched, layer l = rows [l * w_row_stride, +64) of
- *      576 columns.  y_all / a_all: [n_layers][nb, h, w, 64] bf16 (conv outputs before BN; layer outputs).
- *      Running statistics and num_batches_tracked are updated as nn.BatchNorm2d does. ---- */
-typedef struct sisr_trunk_layer {
-  const float* bias;
-  const float* gamma;
-  const float* beta;
-  float* running_mean;
-  float* running_var;
-  long long* nbt;          /* nullable */
-  const float* slope;      /* nullable */
-  float* aux;
-  int residual_layer, reserved;
-} sisr_trunk_layer;
-int sisr_trunk_supported(int nb, int h, int w, int n_layers);
-size_t sisr_trunk_workspace_bytes(int n_layers);
-int sisr_trunk_forward(const sisr_bf16* x0, int nb, int h, int w, const sisr_bf16* weights, int w_row_stride,
-                       const sisr_trunk_layer* layers, int n_layers, sisr_bf16* y_all, sisr_bf16* a_all,
-                       float momentum, float eps, void* workspace, void* stream);
 
 /* ---- convolutions: nn.Conv2d at model_generator.py:10,13,33,39,45,52,123,
  *      model_discriminator.py:10,39 and torchvision vgg19.features (model_content_extractor.py:43) ---- */

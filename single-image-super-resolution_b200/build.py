@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler",
           "-Wall", "-Xcompiler", "-Wno-unused-function"]
-LIB_SOURCES = ["abi.cu", "igemm_tc.cu", "igemm_th.cu", "igemm_pm.cu", "trunk_fused.cu", "wgrad_tc.cu", "conv_simt.cu", "conv_thin.cu", "elementwise.cu", "spectral.cu",
+LIB_SOURCES = ["abi.cu", "igemm_tc.cu", "igemm_pm.cu", "wgrad_tc.cu", "conv_simt.cu", "conv_thin.cu", "elementwise.cu", "spectral.cu",
                "linear.cu", "optim.cu", "peer.cu", "metrics.cu", "tmap.cpp"]
 
 
@@ -57,7 +57,7 @@ def build_lib(force=False, verbose_ptxas=False):
 
 def build_harness():
     out = os.path.join(ROOT, "build", "harness_igemm")
-    srcs = [os.path.join(CSRC, f) for f in ("harness_igemm.cu", "igemm_tc.cu", "igemm_th.cu", "igemm_pm.cu", "conv_simt.cu", "conv_thin.cu", "tmap.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("harness_igemm.cu", "igemm_tc.cu", "igemm_pm.cu", "conv_simt.cu", "conv_thin.cu", "tmap.cpp")]
     if _newer(out, srcs):
         _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-o", out, *srcs, "-lcudart"])
     return out

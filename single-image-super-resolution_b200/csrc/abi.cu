@@ -15,7 +15,6 @@
 #include "optim.h"
 #include "peer.h"
 #include "spectral.h"
-#include "trunk_fused.h"
 #include "wgrad_tc.h"
 
 using namespace sisr;
@@ -70,7 +69,7 @@ const char* sisr_last_error(void) { return g_err; }
 int sisr_abi_version(void) { return 2; }
 int sisr_stats_rows(void) { return igemm_max_ctas(); }
 int sisr_debug_transposed(int on) { igemm_set_transposed(on); return 0; }
-int sisr_debug_th_mode(int on) { igemm_set_th(on); return 0; }
+int sisr_debug_pm_mode(int on) { igemm_set_pm(on); return 0; }
 int sisr_conv_uses_tensor_cores(const sisr_conv_desc* d) { return desc_ok(d) && tc_shape(d) ? 1 : 0; }
 
 // ------------------------------------------------------------------ layout
@@ -469,21 +468,6 @@ int sisr_mse_fwd(const float* a, const float* b, long long n, float coef, float*
 int sisr_mse_bwd(const float* a, const float* b, long long n, float coef, const float* gout, float* ga,
                  float* gb, void* s) {
   return wrap(mse_bwd(a, b, n, coef, gout, ga, gb, S(s)), "mse_bwd");
-}
-
-// ------------------------------------------------------------------ fused persistent trunk forward
-static_assert(sizeof(sisr_trunk_layer) == sizeof(TrunkLayerHost), "sisr_trunk_layer layout");
-int sisr_trunk_supported(int nb, int h, int w, int n_layers) { return trunk_fused_supported(nb, h, w, n_layers) ? 1 : 0; }
-size_t sisr_trunk_workspace_bytes(int n_layers) { return trunk_fused_workspace_bytes(n_layers); }
-int sisr_trunk_forward(const sisr_bf16* x0, int nb, int h, int w, const sisr_bf16* weights, int w_row_stride,
-                       const sisr_trunk_layer* layers, int n_layers, sisr_bf16* y_all, sisr_bf16* a_all,
-                       float momentum, float eps, void* workspace, void* s) {
-  if (!x0 || !weights || !layers || !y_all || !a_all || !workspace) return fail(1, "trunk_forward: null argument");
-  if (int rc = trunk_fused_forward(B(x0), nb, h, w, B(weights), w_row_stride,
-                                   reinterpret_cast<const TrunkLayerHost*>(layers), n_layers, B(y_all), B(a_all),
-                                   momentum, eps, workspace, S(s)))
-    return fail(rc, "trunk_forward: %s", trunk_fused_last_error());
-  return 0;
 }
 
 // ------------------------------------------------------------------ image-quality metrics

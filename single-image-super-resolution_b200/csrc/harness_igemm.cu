@@ -271,6 +271,23 @@ static int run_conv(const ConvCase& cc, bool timing) {
            worst < 1e-3 ? "ok" : "FAIL");
     fail |= !(worst < 1e-3);
   }
+  if (timing && getenv("PM_TIMING")) {
+    long long* dcnt;
+    CK(cudaMalloc(&dcnt, 64));
+    CK(cudaMemset(dcnt, 0, 64));
+    igemm_set_pm_debug(dcnt);
+    const int reps = 10;
+    for (int i = 0; i < reps; ++i) igemm_launch(p, 0);
+    CK(cudaDeviceSynchronize());
+    igemm_set_pm_debug(nullptr);
+    long long h[8];
+    CK(cudaMemcpy(h, dcnt, 64, cudaMemcpyDeviceToHost));
+    if (h[3])
+      printf("[phases %s] CTA 0, cycles per tile: MMA warp waits accumulator %lld, box %lld, issues %lld | epilogue warp per M "
+             "tile: waits %lld, works %lld | kernel %lld cycles, %lld tiles, %lld M tiles\n", cc.name, h[0] / h[3], h[1] / h[3],
+             h[2] / h[3], h[6] ? h[4] / h[6] : 0, h[6] ? h[5] / h[6] : 0, h[7] / reps, h[3] / reps, h[6] / reps);
+    cudaFree(dcnt);
+  }
   if (timing) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -320,49 +337,41 @@ int main(int argc, char** argv) {
       {"c256_512_6x6_n8", 8, 6, 6, 256, 512, 1, 0, ACT_RELU, 0},
       {"c128_256_s2_12x12_n8", 8, 12, 12, 128, 256, 2, 0, ACT_NONE, 1},
   };
-  if (argc > 1 && (argv[1][0] == 't' || argv[1][0] == 'p')) {
-    // halo-fed kernels for the 64 -> 64 channel layers: "harness_igemm th" = weights on M with stacked taps
-    // (igemm_th.cu), "harness_igemm pm [grp]" = pixels on M (igemm_pm.cu)
-    const bool pm = argv[1][0] == 'p';
+  if (argc > 1 && argv[1][0] == 'p') {
+    // halo-fed kernel for the 64 -> 64 channel layers, pixels on M (igemm_pm.cu): "harness_igemm pm [grp]";
+    // PM_TIMING=1 adds the phase counters of CTA 0
     igemm_set_transposed(1);
-    igemm_set_th(1);
-    igemm_set_pm(pm ? 1 : 0);
-    if (pm && argc > 2) igemm_set_pm_grp(atoi(argv[2]));
-    printf("-- halo-fed kernel, %s (64 -> 64)\n", pm ? "pixels on M" : "weights on M, stacked taps");
-    const ConvCase th_cases[] = {
-        {"t_c64_24x24_n4", 4, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
-        {"t_c64_12x12_n3", 3, 12, 12, 64, 64, 1, 0, ACT_PRELU, 1},
-        {"t_c64_9x7_n2_odd", 2, 9, 7, 64, 64, 1, 0, ACT_LEAKY, 1},
-        {"t_c64_48x48_n2", 2, 48, 48, 64, 64, 1, 0, ACT_NONE, 1},
-        {"t_c64_96x96_n3", 3, 96, 96, 64, 64, 1, 0, ACT_RELU, 0},
-        {"t_c64_24x24_n150_multi", 150, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
-        {"t_c64_5x40_n7", 7, 5, 40, 64, 64, 1, 0, ACT_NONE, 1},
+    igemm_set_pm(1);
+    if (argc > 2) igemm_set_pm_grp(atoi(argv[2]));
+    printf("-- halo-fed kernel, pixels on M (64 -> 64)\n");
+    const ConvCase pm_cases[] = {
+        {"p_c64_24x24_n4", 4, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
+        {"p_c64_12x12_n3", 3, 12, 12, 64, 64, 1, 0, ACT_PRELU, 1},
+        {"p_c64_9x7_n2_odd", 2, 9, 7, 64, 64, 1, 0, ACT_LEAKY, 1},
+        {"p_c64_48x48_n2", 2, 48, 48, 64, 64, 1, 0, ACT_NONE, 1},
+        {"p_c64_96x96_n3", 3, 96, 96, 64, 64, 1, 0, ACT_RELU, 0},
+        {"p_c64_24x24_n150_multi", 150, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
+        {"p_c64_5x40_n7", 7, 5, 40, 64, 64, 1, 0, ACT_NONE, 1},
     };
-    for (const auto& cc : th_cases) {
+    for (const auto& cc : pm_cases) {
       IgemmProblem q;
       fill_fprop_problem(q, cc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-      if (pm ? !igemm_pm_supported(q) : !igemm_th_supported(q)) {
+      if (!igemm_pm_supported(q)) {
         printf("[conv %s] NOT routed to the halo-fed kernel\n", cc.name);
         ++fails;
       }
       fails += run_conv(cc, false);
     }
-    const ConvCase th_big[] = {
+    const ConvCase pm_big[] = {
         {"trunk_c64_24x24_n64", 64, 24, 24, 64, 64, 1, 0, ACT_NONE, 1},
         {"vgg_c64_96x96_n64", 64, 96, 96, 64, 64, 1, 0, ACT_RELU, 0},
     };
-    for (const auto& cc : th_big) fails += run_conv(cc, true);
-    if (pm) {
-      igemm_set_pm(0);
-      for (const auto& cc : th_big) fails += run_conv(cc, true);    // same shapes on igemm_th
-    }
-    igemm_set_th(0);
+    for (const auto& cc : pm_big) fails += run_conv(cc, true);
     igemm_set_pm(0);
-    for (const auto& cc : th_big) fails += run_conv(cc, true);      // same shapes on the im2col-fed transposed kernel
+    for (const auto& cc : pm_big) fails += run_conv(cc, true);      // same shapes on the im2col-fed transposed kernel
     printf("harness: %d failure(s)\n", fails);
     return fails ? 1 : 0;
   }
-  igemm_set_th(0);
   igemm_set_pm(0);
   igemm_set_transposed(1);
   printf("-- default engine (transposed tiles for Cout <= 128)\n");

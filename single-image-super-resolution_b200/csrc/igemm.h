@@ -63,18 +63,15 @@ struct IgemmProblem {
 int igemm_launch(const IgemmProblem& p, cudaStream_t stream);
 bool igemm_supported(const IgemmProblem& p);
 void igemm_set_transposed(int on);     // 0: never put the pixels on the UMMA N side (A-B timing)
-// Transposed halo-fed kernel with tap-pair stacking (igemm_th.cu): same-size stride-1 3x3, 64 -> 64 channels.
-// igemm_launch() routes to it first when igemm_th_supported(p).
-bool igemm_th_supported(const IgemmProblem& p);
-int igemm_th_launch(const IgemmProblem& p, cudaStream_t stream);
-void igemm_set_th(int on);             // 0: never use it (A-B timing, SISR_TH=0)
-const char* igemm_th_last_error();
-// Halo-fed kernel with the pixels on the UMMA M side (igemm_pm.cu): the same problems as igemm_th; igemm_launch()
-// tries it before igemm_th.
+// Halo-fed kernel with the pixels on the UMMA M side (igemm_pm.cu): same-size stride-1 3x3, 64 -> 64 channels.
+// igemm_launch() routes to it first when igemm_pm_supported(p).
 bool igemm_pm_supported(const IgemmProblem& p);
 int igemm_pm_launch(const IgemmProblem& p, cudaStream_t stream);
 void igemm_set_pm(int on);             // 0: never use it (A-B timing, SISR_PM=0)
-void igemm_set_pm_grp(int grp);        // M tiles whose instructions are interleaved (0: planner's choice)
+void igemm_set_pm_grp(int grp);
+// harness only: 8 device counters that CTA 0 adds its phase cycles to ({MMA warp: wait accumulator, wait box, issue,
+// tiles}, {epilogue warp 2: wait M tile, work, M tiles}, kernel cycles); nullptr (default) = no instrumentation
+void igemm_set_pm_debug(long long* counters);        // M tiles whose instructions are interleaved (0: planner's choice)
 const char* igemm_pm_last_error();
 int igemm_max_ctas();   // the persistent grid never exceeds this (number of SMs)
 const char* igemm_last_error();

@@ -1,23 +1,24 @@
 // Halo-fed tcgen05 convolution for the 64 -> 64 channel 3x3 layers (stride 1, same size) with the PIXELS on
 // the UMMA M side: the generator trunk (fprop and dgrad: 66 launches per step) and VGG conv1_2.
 //
-// Why not igemm_th (weights on M, two taps stacked, pixels on N)?  Its MMA stream is short (24 full
-// instructions per 320 positions) but its epilogue is not: the accumulator holds channels on the TMEM lanes,
-// so the upper lane half (the stacked tap) must be handed to the lower half through shared memory, every
-// value crosses a lane-pair transpose and a staging tile before it can leave as an NHWC row, and the BN sums
-// are taken per lane.  Measured (trunk_fused phase counters, the same scheme): 9.7k + 2.6k of the conv's 19k
-// cycles per layer are epilogue, 5.7k are MMA.  With the pixels on M
+// Why not weights on M with two stacked taps and the pixels on N (round 2's first scheme, igemm_th, removed)?
+// Its MMA stream is short (24 full instructions per 320 positions) but its epilogue is not: the accumulator
+// holds channels on the TMEM lanes, so the upper lane half (the stacked tap) must be handed to the lower half
+// through shared memory, every value crosses a lane-pair transpose and a staging tile before it can leave as
+// an NHWC row, and the BN sums are taken per lane.  With the pixels on M
 //   * an accumulator row IS an NHWC pixel: each epilogue thread reads 32 channels of its own position from
 //     TMEM and stores 64 contiguous bytes - no hand-over, no transpose, no staging tile, no named barriers;
 //   * one M tile = 128 consecutive box positions x 64 output channels = 64 TMEM columns, so up to 8 tiles
 //     (1024 positions) fit the 512 columns: the epilogue of one tile runs under the MMAs of the others;
-//   * consecutive instructions go to DIFFERENT accumulators (round robin over `grp` M tiles): an N = 64
-//     instruction that accumulates into the columns of its predecessor costs 94 cycles (dependency, not
-//     throughput - profiles/r2_probe_mma.txt); independent ones overlap (same file, SSx2 / SSx4 rows);
-//   * the nine taps are nine start-address shifts of the A descriptor into ONE TMA box with halo (the trick
-//     igemm_th uses on its B side, csrc/probe_shift.cu); the weights (72 KB, nine 64 x 64 K-major tiles) stay
-//     resident in shared memory for all tiles of the CTA.
-// The two halo columns of every box row are computed and discarded (<= 8 %), as in igemm_th.
+//   * the nine taps are nine start-address shifts of the A descriptor into ONE TMA box with halo
+//     (csrc/probe_shift.cu); the weights (72 KB, nine 64 x 64 K-major tiles) stay resident in shared memory
+//     for all tiles of the CTA.
+// Measured with the phase counters below (profiles/r2_pm_phases.txt): the kernel is bound by the MMA stream -
+// the issuing thread is held ~107 cycles per M = 128 x N = 64 x K = 16 instruction (36 per M tile), the epilogue
+// warps work 300-500 cycles per M tile and wait for the rest.  A CTA-pair form (cta_group::2, M = 256, each CTA
+// its own tile and half of the weight rows) was built and passed parity, but its instruction took 186 cycles in
+// this kernel - slower than two single-CTA instructions - and was removed (profiles/r2_notes.md).
+// The two halo columns of every box row are computed and discarded (<= 8 %).
 //
 //   warp 0: TMA producer   warp 1: MMA issuer   warps 2-9: epilogue (warp % 4 = TMEM lane quadrant = 32
 //   positions of the M tile, (warp - 2) / 4 = channel half)
@@ -56,9 +57,11 @@ struct PMParams {
   int stats_rows;
   const __nv_bfloat16* mask;   // nullable, indexed like `out`: stored value = mask > 0 ? v : v * mask_slope
   float mask_slope;
+  long long* dbg;              // nullable (harness only): phase cycle counters of CTA 0, see igemm_set_pm_debug
 };
 
 thread_local char g_err[256] = "";
+long long* g_pm_dbg = nullptr;
 
 // v[0..32) per lane -> lane l holds the sum over the warp of element l (31 shuffles instead of 160)
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
@@ -94,6 +97,7 @@ igemm_pm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const long long k0 = p.dbg ? clock64() : 0;
 
   if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   if (warp == 0 && lane == 0) {
@@ -142,39 +146,60 @@ igemm_pm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: D[position, co] += X_tap * W_tap^T
-    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
-    mbar_wait(smem_u32(&w_bar), 0);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t set = it % p.sets, suse = it / p.sets;
-      const uint32_t bb = it % p.nbox, buse = it / p.nbox;
-      mbar_wait(smem_u32(&tmem_empty_bar[set]), (suse & 1) ^ 1);   // epilogue drained this accumulator set
-      mbar_wait(smem_u32(&box_full[bb]), buse & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t tmem_d = tmem_base + set * p.mt * 64;
-        const uint32_t w_addr = smem_u32(smem_w);
-        const uint32_t x_addr = smem_u32(smem_box + bb * p.box_alloc);
+    {
+      const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(smem_u32(&w_bar), 0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t set = it % p.sets, suse = it / p.sets;
+        const uint32_t bb = it % p.nbox, buse = it / p.nbox;
+        const long long c0 = p.dbg ? clock64() : 0;
+        mbar_wait(smem_u32(&tmem_empty_bar[set]), (suse & 1) ^ 1);   // epilogue(s) drained this accumulator set
+        const long long c1 = p.dbg ? clock64() : 0;
+        mbar_wait(smem_u32(&box_full[bb]), buse & 1);
+        const long long c2 = p.dbg ? clock64() : 0;
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t tmem_d = tmem_base + set * p.mt * 64;
+          const uint32_t w_addr = smem_u32(smem_w);
+          const uint32_t x_addr = smem_u32(smem_box + bb * p.box_alloc);
+          auto issue = [&](int m, int k, int t) {
+            const uint64_t db = umma_smem_desc(w_addr + t * kWTap + k * 32, 16, 1024);
+            const uint64_t da = umma_smem_desc(x_addr + (m * 128 + p.sigma[t]) * 128 + k * 32, 16, 1024);
+            umma_bf16(tmem_d + m * 64, da, db, idesc, (k > 0 || t > 0) ? 1u : 0u);
+          };
+          auto commit = [&](uint32_t bar) { umma_commit(bar); };
 #pragma unroll 1
-        for (int m0 = 0; m0 < p.mt; m0 += p.grp) {
-          const int m1 = m0 + p.grp < p.mt ? m0 + p.grp : p.mt;
+          for (int m0 = 0; m0 < p.mt; m0 += p.grp) {
+            const int m1 = m0 + p.grp < p.mt ? m0 + p.grp : p.mt;
+            // K steps 0-2: consecutive instructions go to different M tiles of the group; last K step: tile by
+            // tile, so that the first tiles of the group are complete (and in the epilogue) while the
+            // instructions of the later ones still run
 #pragma unroll 1
-          for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 3; ++k) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const uint64_t db = umma_smem_desc(w_addr + t * kWTap + k * 32, 16, 1024);
+              for (int t = 0; t < 9; ++t) {
 #pragma unroll 1
-              for (int m = m0; m < m1; ++m) {
-                const uint64_t da = umma_smem_desc(x_addr + (m * 128 + p.sigma[t]) * 128 + k * 32, 16, 1024);
-                umma_bf16(tmem_d + m * 64, da, db, idesc, (k > 0 || t > 0) ? 1u : 0u);
+                for (int m = m0; m < m1; ++m) issue(m, k, t);
               }
             }
+#pragma unroll 1
+            for (int m = m0; m < m1; ++m) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) issue(m, 3, t);
+              commit(smem_u32(&tmem_full_bar[set][m]));
+            }
           }
-          for (int m = m0; m < m1; ++m) umma_commit(smem_u32(&tmem_full_bar[set][m]));
+          commit(smem_u32(&box_empty[bb]));
+          if (p.dbg && blockIdx.x == 0) {
+            p.dbg[0] += c1 - c0;             // MMA warp waits for a free accumulator set
+            p.dbg[1] += c2 - c1;             // ... for the box
+            p.dbg[2] += clock64() - c2;      // ... issues
+            p.dbg[3] += 1;
+          }
         }
-        umma_commit(smem_u32(&box_empty[bb]));
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue
@@ -187,6 +212,7 @@ igemm_pm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
     for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.f;
     uint32_t it = 0;
+    long long t_prev = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t set = it % p.sets, suse = it / p.sets;
       const int per_img = p.tiles_h * p.tiles_w;
@@ -208,7 +234,14 @@ igemm_pm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 4; ++j) mk[j] = __ldg(mp + j);
         }
+        const long long e0 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(&tmem_full_bar[set][m]), suse & 1);
+        if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) {
+          const long long e1 = clock64();
+          p.dbg[4] += e1 - e0;               // epilogue warp 2 waits for an M tile
+          if (t_prev) p.dbg[5] += e0 - t_prev;   // ... works on the previous one (incl. its stores being issued)
+          p.dbg[6] += 1;
+        }
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld_32x32(trow + m * 64, raw);
@@ -251,6 +284,7 @@ igemm_pm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           for (int j = 0; j < 4; ++j)
             reinterpret_cast<uint4*>(dst)[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
         }
+        if (p.dbg) t_prev = clock64();
       }
       tc_fence_before();
       __syncwarp();
@@ -282,6 +316,7 @@ igemm_pm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[7] += clock64() - k0;
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -305,8 +340,8 @@ struct PMPlan {
   double cost;
 };
 
-// Tile = R rows x TW columns = mt M tiles of 128 box positions: minimise waves x (MMA cycles + fixed) per
-// useful pixel over the shapes that fit shared memory (resident weights + one or two boxes) and TMEM.
+// Tile = R rows x TW columns = mt M tiles of 128 box positions: minimise rounds x (MMA cycles + fixed) over the
+// shapes that fit shared memory (resident weights + one or two boxes) and TMEM.
 bool make_plan(const IgemmProblem& p, PMPlan& best) {
   best.cost = -1.0;
   const long long imgs = p.NB;
@@ -322,21 +357,17 @@ bool make_plan(const IgemmProblem& p, PMPlan& best) {
       const int box_alloc = (rows_needed * 128 + 1023) / 1024 * 1024;
       const int tiles_h = (p.H + R - 1) / R;
       const long long tiles = imgs * tiles_h * tiles_w;
-      const long long waves = (tiles + sms() - 1) / sms();
-      const int nbox = waves > 1 ? 2 : 1;
+      const long long rounds = (tiles + sms() - 1) / sms();        // tiles per CTA
+      const int nbox = rounds > 1 ? 2 : 1;
       const int smem = kWBytes + nbox * box_alloc + 1024;
       if (smem > 225 * 1024) continue;
-      const int sets = (waves > 1 && 2 * mt <= kMaxMT) ? 2 : 1;
-      // 36 instructions per M tile; ~50 cycles each when consecutive instructions hit different accumulators,
-      // 94 when a tile stands alone.  With one accumulator set the epilogue of a tile is exposed.
-      const double per_instr = mt >= 2 ? 50.0 : 94.0;
-      const double epi = sets == 2 ? 0.0 : 600.0 * mt;
-      const double c = static_cast<double>(waves) * (36.0 * mt * per_instr + epi + 2000.0);
-      if (best.cost < 0 || c < best.cost) {
-        int grp = mt < 4 ? mt : (mt % 3 == 0 ? 3 : (mt % 2 == 0 ? 2 : 3));
-        if (sets == 2) grp = mt;            // the other set's epilogue already overlaps
-        best = PMPlan{R, TW, mt, sets, grp, box_alloc, nbox, smem, c};
-      }
+      const int sets = (rounds > 1 && 2 * mt <= kMaxMT) ? 2 : 1;
+      // 36 instructions per M tile, ~107 cycles each (measured).  With one accumulator set the epilogue of the
+      // last M tile of a tile is exposed.
+      const double per_instr = 107.0;
+      const double epi = sets == 2 ? 0.0 : 700.0;
+      const double c = static_cast<double>(rounds) * (36.0 * mt * per_instr + epi + 2500.0);
+      if (best.cost < 0 || c < best.cost) best = PMPlan{R, TW, mt, sets, mt < 4 ? mt : 4, box_alloc, nbox, smem, c};
     }
   }
   return best.cost >= 0;
@@ -347,6 +378,7 @@ bool make_plan(const IgemmProblem& p, PMPlan& best) {
 const char* igemm_pm_last_error() { return g_err; }
 void igemm_set_pm(int on) { g_pm_mode = on; }
 void igemm_set_pm_grp(int grp) { g_pm_grp = grp; }
+void igemm_set_pm_debug(long long* counters) { g_pm_dbg = counters; }
 
 bool igemm_pm_supported(const IgemmProblem& p) {
   if (!g_pm_mode) return false;
@@ -396,6 +428,7 @@ int igemm_pm_launch(const IgemmProblem& p, cudaStream_t stream) {
   tp.bias = p.bias; tp.act = p.act; tp.slope = p.slope; tp.slope_ptr = p.slope_ptr;
   tp.stats = p.stats; tp.stats_rows = p.stats_rows;
   tp.mask = p.mask; tp.mask_slope = p.mask_slope;
+  tp.dbg = g_pm_dbg;
   static int configured = 0;
   if (pl.smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(igemm_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);

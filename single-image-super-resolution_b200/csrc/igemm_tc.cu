@@ -11,7 +11,7 @@
 //
 // The A (activation) operand comes from im2col-mode TMA: one 128 pixel x 64 channel tile per (tap, channel
 // block).  That handles every geometry (stride 2, dgrad through PixelShuffle, parity-split dgrad).  The 64 -> 64
-// channel stride-1 layers take the halo-fed kernel of igemm_th.cu instead (one TMA box per tile, stacked taps).
+// channel stride-1 layers take the halo-fed kernel of igemm_pm.cu instead (one TMA box per tile, pixels on M).
 // Measured and removed (notes: profiles/r1_notes.md, profiles/r2_notes.md): a halo-box feed for these
 // 128-pixel tiles (no gain: the thin layers sat on the per-instruction floor) and a CTA-pair kernel
 // (cta_group::2, M = 256: validated, 4-10 % slower than this kernel on the 256 / 512-channel layers).
@@ -738,11 +738,6 @@ int igemm_launch(const IgemmProblem& p, cudaStream_t stream) {
   if (igemm_pm_supported(p)) {
     const int rc = igemm_pm_launch(p, stream);
     if (rc) snprintf(g_err, sizeof g_err, "%s", igemm_pm_last_error());
-    return rc;
-  }
-  if (igemm_th_supported(p)) {
-    const int rc = igemm_th_launch(p, stream);
-    if (rc) snprintf(g_err, sizeof g_err, "%s", igemm_th_last_error());
     return rc;
   }
   const bool flat_out = p.osy == 1 && p.osx == 1 && p.opy == 0 && p.opx == 0 && p.OH == p.GH && p.OW == p.GW;

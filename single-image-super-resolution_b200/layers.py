@@ -53,14 +53,14 @@ class SNConv2d(nn.Module):
         return self.weight_orig if self.sn else self.weight
 
     def run(self, x: torch.Tensor, *, act: int = ACT_NONE, slope: Optional[torch.Tensor] = None,
-            ps_r: int = 0, want_stats: bool = False, out_nchw_f32: bool = False, pre_y=None):
-        """x: NHWC bf16.  Returns (y, stats).  ``pre_y``: output already computed by the fused trunk kernel."""
+            ps_r: int = 0, want_stats: bool = False, out_nchw_f32: bool = False):
+        """x: NHWC bf16.  Returns (y, stats)."""
         cfg = ConvCfg(stride=self.stride, pad=self.padding, act=act, ps_r=ps_r,
                       want_stats=want_stats, training=self.training, out_nchw_f32=out_nchw_f32)
         u = self.weight_u if self.sn else None
         v = self.weight_v if self.sn else None
         prep, self._prep = self._prep, None      # set by ops.prepare_convs for exactly one forward
-        return Conv2dFn.apply(x, self.master_weight, self.bias, u, v, slope, cfg, prep, pre_y)
+        return Conv2dFn.apply(x, self.master_weight, self.bias, u, v, slope, cfg, prep)
 
     def forward(self, x):  # module-boundary use: NCHW fp32 in / out
         y, _ = self.run(ops.ToNHWC.apply(x))
@@ -72,12 +72,11 @@ class SNConv2d(nn.Module):
 
 
 def bn_act(bn: nn.BatchNorm2d, y: torch.Tensor, stats, *, act: int = ACT_NONE,
-           slope: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, pre=None):
-    """Apply the BatchNorm held by ``bn`` (+activation, +residual) to NHWC bf16 ``y``.  ``pre`` = (output,
-    saved statistics) already computed by the fused trunk kernel."""
+           slope: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None):
+    """Apply the BatchNorm held by ``bn`` (+activation, +residual) to NHWC bf16 ``y``."""
     cfg = BnCfg(act=act, training=bn.training, momentum=bn.momentum, eps=bn.eps)
     return BnActFn.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                         bn.num_batches_tracked, residual, slope, cfg, pre)
+                         bn.num_batches_tracked, residual, slope, cfg)
 
 
 __all__ = ["SNConv2d", "bn_act", "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ACT_PRELU", "ACT_TANH"]

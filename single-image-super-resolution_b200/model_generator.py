@@ -31,15 +31,12 @@ class BasicBlock(nn.Module):
             SNConv2d(n_features, n_features, 3, 1, 1, sn=True),
             nn.BatchNorm2d(n_features))
 
-    def forward_nhwc(self, x, fused=None):
-        """``fused``: [(y, out, aux)] x 2 from ops.trunk_forward_fused - the two layers' results, adopted by the
-        autograd operators instead of launching their forward kernels (the backward pass is unchanged)."""
+    def forward_nhwc(self, x):
         c1, bn1, act, c2, bn2 = self.layers
-        f1, f2 = fused if fused is not None else (None, None)
-        y, st = c1.run(x, want_stats=bn1.training, pre_y=f1[0] if f1 else None)
-        a = bn_act(bn1, y, st, act=ACT_PRELU, slope=act.weight, pre=f1[1:] if f1 else None)
-        y, st = c2.run(a, want_stats=bn2.training, pre_y=f2[0] if f2 else None)
-        return bn_act(bn2, y, st, residual=x, pre=f2[1:] if f2 else None)
+        y, st = c1.run(x, want_stats=bn1.training)
+        a = bn_act(bn1, y, st, act=ACT_PRELU, slope=act.weight)
+        y, st = c2.run(a, want_stats=bn2.training)
+        return bn_act(bn2, y, st, residual=x)
 
     def forward(self, x):
         return ops.ToNCHW.apply(self.forward_nhwc(ops.ToNHWC.apply(x)))
@@ -131,22 +128,11 @@ class Generator(nn.Module):
         conv0, act0 = self.first_layers
         x, _ = conv0.run(x, act=ACT_PRELU, slope=act0.weight)
         skip = ops.tap(tap_prefix + "first_layers", x)
+        for i, block in enumerate(self.block_list):
+            x = ops.tap(f"{tap_prefix}block_list.{i}", block.forward_nhwc(x))
         conv_e, bn_e = self.block_list_end
-        # single GPU, train mode: the whole trunk in one persistent kernel; the per-layer operators below then
-        # only record the autograd graph around its results
-        specs = []
-        for i, block in enumerate(self.block_list):
-            c1, bn1, act, c2, bn2 = block.layers
-            specs += [(c1, bn1, act.weight, -1), (c2, bn2, None, -2 if i == 0 else 2 * i - 1)]
-        specs.append((conv_e, bn_e, None, -2))
-        fused = ops.trunk_forward_fused(skip, specs)
-        res, keep = fused if fused is not None else (None, None)
-        for i, block in enumerate(self.block_list):
-            x = ops.tap(f"{tap_prefix}block_list.{i}",
-                        block.forward_nhwc(x, (res[2 * i], res[2 * i + 1]) if res else None))
-        fe = res[-1] if res else None
-        y, st = conv_e.run(x, want_stats=bn_e.training, pre_y=fe[0] if fe else None)
-        x = ops.tap(tap_prefix + "block_list_end", bn_act(bn_e, y, st, residual=skip, pre=fe[1:] if fe else None))
+        y, st = conv_e.run(x, want_stats=bn_e.training)
+        x = ops.tap(tap_prefix + "block_list_end", bn_act(bn_e, y, st, residual=skip))
         for s, stage in enumerate(self.upscale):
             x = ops.tap(f"{tap_prefix}upscale.{s}", stage.forward_nhwc(x))
         return x

@@ -397,78 +397,6 @@ def prepare_convs(convs, first_needs_dx: bool):
     call("sisr_weight_prep_batched", ctypes.addressof(arr), len(prep_rows), st)
 
 
-# ----------------------------------------------------------------------------- fused persistent trunk
-class _TrunkLayerC(ctypes.Structure):
-    """struct sisr_trunk_layer"""
-    _fields_ = [(n, ctypes.c_void_p) for n in ("bias", "gamma", "beta", "running_mean", "running_var", "nbt",
-                                               "slope", "aux")] + [("residual_layer", ctypes.c_int),
-                                                                   ("reserved", ctypes.c_int)]
-
-
-_fused_trunk = [os.environ.get("SISR_FUSED_TRUNK", "1") != "0"]
-
-
-def set_fused_trunk(on: bool):
-    """False: the generator trunk runs layer by layer (conv, finalize, normalise kernels) - A-B tests / timing."""
-    _fused_trunk[0] = bool(on)
-
-
-def trunk_forward_fused(x0: torch.Tensor, specs):
-    """All conv3x3(64->64) + train-mode BatchNorm (+PReLU / +residual) layers of the generator trunk in ONE
-    persistent cooperative launch (csrc/trunk_fused.cu).  ``specs``: per layer (conv, bn, prelu_weight | None,
-    residual_layer) with residual_layer -1 none, -2 = x0, l' = output of layer l'; every conv has been through
-    ``prepare_convs`` in the same call.  Returns [(y, out, aux)] per layer - the tensors the per-layer autograd
-    operators then adopt instead of launching their forward kernels - or None when the fused kernel does not
-    apply (eval mode, SyncBN active, geometry): the caller falls back to the per-layer path."""
-    if not _fused_trunk[0] or not specs or not x0.is_cuda or x0.dtype != torch.bfloat16:
-        return None
-    if _world() > 1:                       # SyncBN: the cross-GPU exchange is not inside the fused kernel
-        return None
-    n, h, w, c = x0.shape
-    L = len(specs)
-    if c != 64 or not query("sisr_trunk_supported", n, h, w, L):
-        return None
-    base = None
-    stride_rows = None
-    for l, (conv, bn, slope, res) in enumerate(specs):
-        if (conv.in_channels != 64 or conv.out_channels != 64 or conv.kernel_size != 3 or conv.stride != 1 or
-                conv.padding != 1 or conv._prep is None or len(conv._prep) != 6 or not bn.training or
-                not conv.training or bn.num_features != 64 or bn.momentum is None):
-            return None
-        wf = conv._prep[0]
-        if l == 0:
-            base = wf
-        else:
-            delta = wf.data_ptr() - base.data_ptr()
-            if delta % (576 * 2 * l) or delta <= 0:
-                return None
-            rows = delta // (576 * 2 * l)
-            if stride_rows is None:
-                stride_rows = rows
-            elif rows != stride_rows:
-                return None                 # prepared weights not equally spaced: no single tensor map
-    if stride_rows is None:
-        stride_rows = 64
-    dev = x0.device
-    x0 = x0.contiguous()
-    y_all = torch.empty((L, n, h, w, 64), dtype=torch.bfloat16, device=dev)
-    a_all = torch.empty((L, n, h, w, 64), dtype=torch.bfloat16, device=dev)
-    aux_all = torch.empty((L, 4, 64), dtype=torch.float32, device=dev)
-    ws = torch.empty(query("sisr_trunk_workspace_bytes", L), dtype=torch.uint8, device=dev)
-    rows = []
-    for l, (conv, bn, slope, res) in enumerate(specs):
-        bias = conv._prep[5]
-        rows.append(_TrunkLayerC(bias.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
-                                 bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
-                                 bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None,
-                                 slope.data_ptr() if slope is not None else None, aux_all[l].data_ptr(), int(res), 0))
-    arr = (_TrunkLayerC * L)(*rows)
-    call("sisr_trunk_forward", x0, n, h, w, base, int(stride_rows), ctypes.addressof(arr), L, y_all, a_all,
-         float(specs[0][1].momentum), float(specs[0][1].eps), ws, _stream())
-    _lib.LAUNCHES[0] += 0
-    return [(y_all[l], a_all[l], aux_all[l]) for l in range(L)], (ws, x0)
-
-
 # ----------------------------------------------------------------------------- convolution
 @dataclass(frozen=True)
 class ConvCfg:
@@ -497,7 +425,7 @@ class Conv2dFn(torch.autograd.Function):
     ``u``/``v`` are given).  Returns (y, stats)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, u, v, slope, cfg: ConvCfg, prepared=None, pre_y=None):
+    def forward(ctx, x, weight, bias, u, v, slope, cfg: ConvCfg, prepared=None):
         _require_cuda(x, "Conv2dFn")
         x = x.contiguous()
         dev = x.device
@@ -525,11 +453,8 @@ class Conv2dFn(torch.autograd.Function):
                 bias_used = torch.empty_like(bias)
             call("sisr_weight_prep", weight, sigma, bias, wf, wd, bias_used if cfg.ps_r == 2 else None,
                  cout, cin, k, cfg.ps_r, st)
-        stats = torch.empty((stats_rows(), 2 * cout), dtype=torch.float32, device=dev) \
-            if (cfg.want_stats and pre_y is None) else None
-        if pre_y is not None:
-            y = pre_y                      # computed by the fused trunk kernel (trunk_forward_fused)
-        elif cfg.out_nchw_f32:
+        stats = torch.empty((stats_rows(), 2 * cout), dtype=torch.float32, device=dev) if cfg.want_stats else None
+        if cfg.out_nchw_f32:
             y = torch.empty((d.n, cout, d.oh, d.ow), dtype=torch.float32, device=dev)
             call("sisr_conv_fprop", d, x, wf, bias_used, cfg.act, cfg.leaky_slope, slope, None, y, None, st)
         else:
@@ -572,7 +497,7 @@ class Conv2dFn(torch.autograd.Function):
         st = _stream()
         cout, cin, k, _ = weight.shape
         if gy is None:                        # only the statistics were used downstream
-            return (None,) * 9
+            return (None,) * 8
         gy = gy.contiguous()
         dslope = colsum = None
         if cfg.out_nchw_f32:
@@ -647,7 +572,7 @@ class Conv2dFn(torch.autograd.Function):
                 dw = None
             if not ctx.needs_input_grad[2]:
                 db = None
-        return dx, dw, db, None, None, dslope, None, None, None
+        return dx, dw, db, None, None, dslope, None, None
 
 
 # ----------------------------------------------------------------------------- BatchNorm (+act, +residual)
@@ -666,22 +591,13 @@ class BnActFn(torch.autograd.Function):
     ``y`` from the producing conv's epilogue (computed here when None)."""
 
     @staticmethod
-    def forward(ctx, y, stats, gamma, beta, running_mean, running_var, nbt, residual, slope, cfg: BnCfg, pre=None):
+    def forward(ctx, y, stats, gamma, beta, running_mean, running_var, nbt, residual, slope, cfg: BnCfg):
         y = y.contiguous()
         dev = y.device
         c = y.shape[-1]
         rows = y.numel() // c
         st = _stream()
         count = float(rows)
-        if pre is not None:
-            # normalised output, saved statistics and the running-statistics update all come from the fused
-            # trunk kernel (single GPU, train mode)
-            out, aux = pre
-            ctx.cfg, ctx.count = cfg, count
-            ctx.has_residual = residual is not None
-            ctx.skip_params = _skip_param_grads
-            ctx.save_for_backward(y, aux, slope)
-            return out
         if cfg.training:
             if stats is None:
                 stats = torch.empty((1, 2 * c), dtype=torch.float32, device=dev)
@@ -759,7 +675,7 @@ class BnActFn(torch.autograd.Function):
             if slope is not None and ctx.needs_input_grad[8]:
                 dslope = local[2 * c:2 * c + 1].clone()
         dres = gout if (ctx.has_residual and ctx.needs_input_grad[7]) else None
-        return dy, None, dgamma, dbeta, None, None, None, dres, dslope, None, None
+        return dy, None, dgamma, dbeta, None, None, None, dres, dslope, None
 
 
 # ----------------------------------------------------------------------------- pooling

@@ -510,7 +510,11 @@ def test_host_feed_pipeline_matches_direct_replay(cuda, golden_dir):
     keys = ("err_d", "err_g_adv", "err_g_cont")
     res = []
     for mode in ("direct", "feed"):
-        tr, _ = _build_step(m, g["seed"], g["shape"], g["features"], g["strides"], g["mask"], g["lr"])
+        # lr 1e-5 (config.py:38), not the golden's 1e-3: the test is about the inputs the pipeline delivers.  Two
+        # runs of the same step differ in the last bits of a few fp32 reductions (atomics), Adam's first updates
+        # are sign-like, and at lr = 1e-3 that alone moved err_g_adv of the SECOND step by 0.1 ... 17 % between
+        # two identical runs (tools/determinism_check.py, profiles/r2_determinism.txt)
+        tr, _ = _build_step(m, g["seed"], g["shape"], g["features"], g["strides"], g["mask"], 1e-5)
         lr0 = m.lr_from_hr(hrs[0].cuda(), (g["LR"], g["LR"]))
         tr.capture(hrs[0].cuda(), lr0, warmup=1)
         outs = []
@@ -531,8 +535,8 @@ def test_host_feed_pipeline_matches_direct_replay(cuda, golden_dir):
             with pytest.raises(RuntimeError):
                 feed.take()
         res.append(outs)
-    # same kernels and inputs; fp32 atomics reorder sums, and at the golden's lr = 1e-3 the sign-like Adam
-    # updates amplify that from step to step (measured 2.5-3.2 % at the 4th step, round 2)
+    # same kernels and inputs; fp32 atomics reorder sums and the sign-like Adam updates amplify that from step
+    # to step
     for i, (a, b) in enumerate(zip(res[0], res[1])):
         for x, y in zip(a, b):
             assert abs(x - y) <= (5e-3 if i == 0 else 2e-2 if i == 1 else 6e-2) * abs(x) + 1e-6, (i, a, b)

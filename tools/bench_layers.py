@@ -87,8 +87,8 @@ def run(kind, name, h, cin, cout, stride, ps, stats):
 
 
 def main():
-    if os.environ.get("TH_MODE"):
-        _lib.query("sisr_debug_th_mode", int(os.environ["TH_MODE"]))
+    if os.environ.get("PM_MODE"):
+        _lib.query("sisr_debug_pm_mode", int(os.environ["PM_MODE"]))
     if os.environ.get("TRANSPOSED"):
         _lib.query("sisr_debug_transposed", int(os.environ["TRANSPOSED"]))
     kinds = ["fprop", "dgrad", "wgrad"] if len(sys.argv) < 2 or sys.argv[1] == "all" else [sys.argv[1]]

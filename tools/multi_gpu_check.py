@@ -31,9 +31,6 @@ def build(dev, grad_sync, seed=800, shape=(3, 32, 32), feats=(64, 64, 128, 128),
 
 
 def main():
-    # the single-process reference of this check runs layer by layer unless asked otherwise: the check is about
-    # the data-parallel exchanges, not about the fused trunk kernel (tests/test_gpu_depth16.py covers that)
-    ops.set_fused_trunk(os.environ.get("MGC_FUSED", "0") == "1")
     rank, local, world = parallel.init_distributed()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)

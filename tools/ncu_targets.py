@@ -80,7 +80,7 @@ def dhead():
 
 
 def main():
-    conv(24, 64, 64, stats=True)                       # generator trunk: igemm_th, wgrad_tc + reduce_finish_small
+    conv(24, 64, 64, stats=True)                       # generator trunk: igemm_pm, wgrad_tc + reduce_finish_small
     conv(96, 64, 64, kinds=("fprop", "dgrad"))         # VGG conv1_2
     conv(48, 128, 128, kinds=("fprop", "dgrad"))       # VGG conv2_2: igemm_t_kernel
     conv(24, 256, 256)                                 # VGG conv3_x / D: igemm_tc_kernel<256,4>, wide wgrad
