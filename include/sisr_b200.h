@@ -137,6 +137,9 @@ int sisr_conv_wgrad_fused(const sisr_conv_desc* d, const sisr_bf16* x, const sis
                           void* stream);
 /* debug: 1 = never use the cooperative launch (two ordinary kernels instead) */
 int sisr_debug_disable_cooperative(int off);
+/* tools only (tools/wgrad_phases.py): 8 int64 DEVICE counters that CTA 0 of every tensor-core weight-gradient launch
+ * adds its phase cycles to; NULL (default) switches the instrumentation off */
+int sisr_debug_wgrad_counters(long long* device_counters);
 
 /* ---- BatchNorm2d (train / eval) fused with PReLU / LeakyReLU / residual add:
  *      model_generator.py:11-14,16-19,40,93 and model_discriminator.py:11-12 ---- */

@@ -373,6 +373,7 @@ int sisr_conv_wgrad_fused(const sisr_conv_desc* d, const sisr_bf16* x, const sis
               "weight_grad_finish");
 }
 int sisr_debug_disable_cooperative(int off) { weight_grad_disable_cooperative(off); return 0; }
+int sisr_debug_wgrad_counters(long long* device_counters) { wgrad_tc_set_debug(device_counters); return 0; }
 
 // ------------------------------------------------------------------ BatchNorm / activations / pooling
 int sisr_bn_stats(const sisr_bf16* y, long long rows, int c, float* stats, void* s) {

@@ -30,7 +30,7 @@ constexpr int kSlots = 11;                    // 9 taps + 1 unused (pair of tap 
 constexpr int kStageBytes = kSlots * kTile;   // 88 KB
 constexpr int kStages = 2;                    // (32-pixel k-blocks x 4 stages and a halo-box feed measured no
                                               // faster, profiles/r1_notes.md: bound by the N = 64 instruction floor)
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                 // TMA warp, MMA warp, 8 epilogue warps (quadrant x column half)
 constexpr int kPairs = 5;
 constexpr int kTmemCols = 512;
 
@@ -42,9 +42,11 @@ struct WParams {
   int ps;                // dY stored pixel-shuffled
   int atomic;            // 1: every split adds into ONE zeroed [Cout][9][Cin] buffer (red.global.add.f32)
   float* out;            // [splits][Cout][9][Cin] (splits > 1) or final [Cout][9][Cin]
+  long long* dbg;        // nullable (tools/wgrad_phases.py): phase cycle counters of CTA 0, see wgrad_tc_set_debug
 };
 
 thread_local char g_err[256] = "";
+long long* g_wgrad_dbg = nullptr;
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
@@ -67,6 +69,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(p.total_kb, kb0 + p.kb_per_split);
   const int num_kb = kb1 - kb0;
+  const long long k0 = p.dbg ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -93,7 +96,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % kStages;
         const uint32_t round = i / kStages;
+        const long long w0 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);
+        if (p.dbg && blockIdx.x == 0) p.dbg[0] += clock64() - w0;      // producer waits for a free stage
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, 10 * kTile);
         const int p0 = (kb0 + i) * kPix;
@@ -118,7 +123,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int i = 0; i < num_kb; ++i) {
       const int s = i % kStages;
       const uint32_t round = i / kStages;
+      const long long c0 = p.dbg ? clock64() : 0;
       mbar_wait(smem_u32(&full_bar[s]), round & 1);
+      const long long c1 = p.dbg ? clock64() : 0;
       tc_fence_after();
       if (lane == 0) {
         const uint32_t base = smem_u32(smem + s * kStageBytes);
@@ -136,21 +143,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         }
         umma_commit(smem_u32(&empty_bar[s]));
         if (i == num_kb - 1) umma_commit(smem_u32(&tmem_full_bar));
+        if (p.dbg && blockIdx.x == 0) {
+          p.dbg[1] += c1 - c0;              // MMA warp waits for the operands of a k-block
+          p.dbg[2] += clock64() - c1;       // ... issues its 20 instructions
+          p.dbg[3] += 1;
+        }
       }
       __syncwarp();
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;          // which 32 of the 64 output channels of every tap pair
     const int row = quad * 32 + lane;          // accumulator row: tap parity * 64 + ci
     const int ci = cib * 64 + (row & 63);
     mbar_wait(smem_u32(&tmem_full_bar), 0);
+    const long long e0 = p.dbg ? clock64() : 0;
     tc_fence_after();
     float* outp = p.out + (p.atomic ? 0 : static_cast<size_t>(split) * p.Cout * 9 * p.Cin);
 #pragma unroll 1
     for (int q = 0; q < kPairs; ++q) {
       const int tap = 2 * q + (row >> 6);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = half;
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + q * 64 + c * 32, raw);
         tmem_ld_wait();
@@ -174,9 +188,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         }
       }
     }
+    if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[4] += clock64() - e0;   // epilogue (stores issued)
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.dbg[5] += clock64() - k0;
+    p.dbg[6] += 1;
+    p.dbg[7] = gridDim.x;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -252,7 +272,10 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long long
   for (int i = threadIdx.x; i < classes * C; i += blockDim.x) atomicAdd(&dbias[i], s_acc[i]);
 }
 
-constexpr long long kAtomicMaxFloats = 1 << 18;      // gradients up to 1 MB accumulate with L2 reductions
+// gradients up to this many floats accumulate with L2 reductions: every layer of the step (the largest, 512 x 512
+// x 9, is 9.4 MB and stays L2-resident).  1 MB (trunk only) -> all: step 8.09 -> 7.95 ms sustained;
+// SISR_WGRAD_ATOMIC_MAX overrides for A-B timing
+const long long kAtomicMaxFloats = [] { const char* e = getenv("SISR_WGRAD_ATOMIC_MAX"); return e ? atoll(e) : (1ll << 22); }();
 int g_wgrad_atomic = [] { const char* e = getenv("SISR_WGRAD_ATOMIC"); return e && e[0] == '0' ? 0 : 1; }();
 
 struct Plan {
@@ -297,6 +320,7 @@ Plan make_plan(int n, int oh, int ow, int cin, int cout, int stride = 0, int ps 
 }  // namespace
 
 const char* wgrad_tc_last_error() { return g_err; }
+void wgrad_tc_set_debug(long long* counters) { g_wgrad_dbg = counters; }
 
 bool wgrad_tc_supported(int n, int h, int w, int cin, int oh, int ow, int cout, int k, int stride,
                         int pad, int ps_r) {
@@ -347,6 +371,7 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
   p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.total_kb = pl.total_kb;
   p.Cin = cin; p.Cout = cout; p.ps = ps;
   p.atomic = pl.atomic;
+  p.dbg = g_wgrad_dbg;
   p.out = (pl.splits > 1 || keep_partials) ? static_cast<float*>(workspace) : g;
   const int smem_bytes = kStages * kStageBytes + 1024;
   static bool configured = false;

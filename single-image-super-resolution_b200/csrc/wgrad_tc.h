@@ -17,5 +17,8 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* g, f
                     void* workspace, int n, int h, int w, int cin, int oh, int ow, int cout, int stride,
                     int ps_r, cudaStream_t s, int* splits_out = nullptr);
 const char* wgrad_tc_last_error();
+// tools only: 8 device counters that CTA 0 adds its phase cycles to ({producer waits stage, MMA warp waits operands,
+// MMA warp issues, k-blocks, epilogue, kernel cycles, launches, grid}); nullptr (default) = no instrumentation
+void wgrad_tc_set_debug(long long* counters);
 
 }  // namespace sisr
