@@ -230,7 +230,10 @@ def build_trainer(dev, batch, world, grad_sync=None, config="x4"):
         for net in (net_g, net_d, ext):
             parallel.broadcast_module(net)
     # with a GradSync the trainer broadcasts weights + buffers and attaches both optimizers itself
-    return m.SRGANTrainer(net_g, net_d, ext, m.StepConfig(lr=1e-5, use_replay=False), grad_sync=grad_sync)
+    cfg_step = m.StepConfig(lr=1e-5, use_replay=False)
+    if os.environ.get("SISR_OVERLAP") == "0":       # A-B timing: D(real) and MaskedVGG(fake) on the main stream
+        cfg_step.overlap_d_real = cfg_step.overlap_fake_features = False
+    return m.SRGANTrainer(net_g, net_d, ext, cfg_step, grad_sync=grad_sync)
 
 
 DP_GOLDEN = os.path.join(ROOT, "profiles", "r2_dp_check_n1.json")

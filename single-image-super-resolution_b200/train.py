@@ -76,6 +76,10 @@ class StepConfig:
     use_replay: bool = True
     async_weight_grads: bool = True     # weight-gradient kernels on a side stream (ops.async_weight_grads)
     overlap_real_features: bool = True  # MaskedVGG(real) on a side stream, concurrent with G and the D update
+    overlap_d_real: bool = True         # D(real) forward (and, through autograd, its backward) on a side stream:
+                                        # it needs nothing from G, so it runs under G's latency-bound forward
+    overlap_fake_features: bool = True  # MaskedVGG(fake) forward / backward on a side stream, concurrent with the
+                                        # D update and the D pass of the G update
 
 
 class SRGANTrainer:
@@ -104,6 +108,11 @@ class SRGANTrainer:
         self._pool = None
         self._side = None
         self._zero = None
+        # parameters of D receive gradients from two streams by design (overlap_d_real): autograd's advice about
+        # the accumulation stream does not apply
+        warn_off = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if warn_off is not None and self.cfg.overlap_d_real:
+            warn_off(False)
 
     def weights(self, epoch: int = 0):
         """(lw_adv_d, lw_adv_g, lw_cont, extractor kind) for ``epoch`` (config.py:136-164)."""
@@ -117,9 +126,11 @@ class SRGANTrainer:
         return val(c.loss_weight_adv_d), val(c.loss_weight_adv_g), cont[0], cont[1]
 
     # -- losses (train.py:128-186) -----------------------------------------------------------
-    def adversarial_loss_d(self, real, curr_fake, old_fakes):
+    def adversarial_loss_d(self, real, curr_fake, old_fakes, d_real=None):
+        """``d_real``: D(real) already computed (on a side stream that the current one has waited for)."""
         c = self.cfg
-        d_real = self.net_d(real).view(-1)
+        if d_real is None:
+            d_real = self.net_d(real).view(-1)
         err, d_x = ops.bce_loss(d_real, c.real_label_reduced)
         d_g_z1 = 0
         for fk in [curr_fake, *old_fakes]:
@@ -135,18 +146,21 @@ class SRGANTrainer:
         err, d_g_z2 = ops.bce_loss(out, self.cfg.real_label)
         return d_g_z2, err
 
-    def content_loss_g(self, real, fake, feat_real=None, kind="features"):
+    def content_loss_g(self, real, fake, feat_real=None, kind="features", feat_fake=None):
         """train.py:183-186; ``kind`` "identity" = model_content_extractor.identity(): pixel MSE."""
         if kind == "identity":
             return ops.mse_loss(real, fake)
         a = self.extractor(real) if feat_real is None else feat_real
-        b = self.extractor(fake)
+        b = self.extractor(fake) if feat_fake is None else feat_fake
         return ops.mse_loss(a, b)
 
-    def _side_stream(self):
+    def _side_stream(self, which: int = 0):
+        """0: MaskedVGG(real), 1: D(real), 2: MaskedVGG(fake)."""
         if self._side is None:
-            self._side = torch.cuda.Stream()
-        return self._side
+            self._side = {}
+        if which not in self._side:
+            self._side[which] = torch.cuda.Stream()
+        return self._side[which]
 
     # -- one iteration -----------------------------------------------------------------------
     def step(self, img_hr: torch.Tensor, img_lr: torch.Tensor, old_fakes=(), epoch: int = 0, img_hr2=None):
@@ -178,17 +192,42 @@ class SRGANTrainer:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side), torch.no_grad():
                 feat_real = self.extractor(cont_real)
+        # D(real) needs nothing from G either.  Its forward runs on a second side stream under G's forward (a
+        # latency-bound chain of small kernels); autograd then runs its backward on that stream too, next to the
+        # backward of the D(fake) pass.  D(fake) starts only after D(real) has finished: the spectral-norm vectors
+        # and BN running statistics advance in the reference's order (train.py:133-141).
+        d_real = d_side = None
+        if lw_d and c.overlap_d_real and img_hr.is_cuda:
+            self.net_d.zero_grad(set_to_none=True)
+            d_side = self._side_stream(1)
+            d_side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(d_side):
+                d_real = self.net_d(real_d).view(-1)
         fake = self.net_g(img_lr)
         curr_fake = fake.detach()
+        # ... and MaskedVGG(fake) does not depend on the D update: forward now, on a third side stream, concurrent
+        # with the D update and the D pass of the G update; its backward (autograd: same stream) runs next to the
+        # data-gradient pass through D
+        feat_fake = f_side = None
+        if lw_c and kind == "features" and c.overlap_fake_features and not on_lr and img_hr.is_cuda:
+            f_side = self._side_stream(2)
+            f_side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(f_side):
+                feat_fake = self.extractor(fake)
 
         d_g_z1 = d_x = d_g_z2 = self._zero
         err_d = err_g_adv = err_g_cont = self._zero
         if lw_d:
-            self.net_d.zero_grad(set_to_none=True)
-            d_g_z1, d_x, err_d = self.adversarial_loss_d(real_d, curr_fake, old_fakes)
+            if d_side is not None:
+                torch.cuda.current_stream().wait_stream(d_side)
+            else:
+                self.net_d.zero_grad(set_to_none=True)
+            d_g_z1, d_x, err_d = self.adversarial_loss_d(real_d, curr_fake, old_fakes, d_real=d_real)
             err_d = err_d * lw_d
             with ops.async_weight_grads(c.async_weight_grads):
                 err_d.backward()
+            if d_side is not None:       # (the backward of the D(real) pass ran there)
+                torch.cuda.current_stream().wait_stream(d_side)
             if self.grad_sync is not None:
                 self.grad_sync.sync(self.opt_d)
             self.opt_d.step()
@@ -199,12 +238,16 @@ class SRGANTrainer:
             err_g_adv = err_g_adv * lw_g
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
+        if f_side is not None:
+            torch.cuda.current_stream().wait_stream(f_side)
         if lw_c:
             cont_fake = lr_from_hr(fake, tuple(img_lr.shape[-2:])) if on_lr else fake
-            err_g_cont = self.content_loss_g(cont_real, cont_fake, feat_real, kind) * lw_c
+            err_g_cont = self.content_loss_g(cont_real, cont_fake, feat_real, kind, feat_fake) * lw_c
         if lw_g or lw_c:
             with ops.async_weight_grads(c.async_weight_grads):
                 (err_g_adv + err_g_cont).backward()
+            if f_side is not None:       # (the backward of MaskedVGG(fake) ran there)
+                torch.cuda.current_stream().wait_stream(f_side)
             if self.grad_sync is not None:
                 self.grad_sync.sync(self.opt_g)
             self.opt_g.step()

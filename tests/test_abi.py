@@ -105,7 +105,7 @@ def test_bench_reads_dominant_kernel_share_from_committed_profile():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     text = mod.dominant_share()
-    assert text.startswith("igemm_t") and "%" in text and "launches" in text and "profiles/" in text
+    assert text.startswith(("igemm_t", "igemm_pm")) and "%" in text and "launches" in text and "profiles/" in text
 
 
 def test_bench_configs_and_traffic_source():
