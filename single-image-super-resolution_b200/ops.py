@@ -173,6 +173,15 @@ def set_grad_ready_callback(fn):
     _grad_ready_cb[0] = fn
 
 
+_before_join_cb = [None]
+
+
+def set_before_join_callback(fn):
+    """``fn()`` runs at the end of a backward pass, after the current stream has waited for the weight-gradient
+    stream and before the gradients still pending there are handed over (parallel.GradSync: see its ``drain``)."""
+    _before_join_cb[0] = fn
+
+
 def _deliver(entry):
     weight, bias, dw, db, want_w, want_b = entry
     for p, g, want in ((weight, dw, want_w), (bias, db, want_b)):
@@ -204,6 +213,8 @@ def join_wgrad(end_of_backward: bool = True):
     _async["keep"].clear()
     if not end_of_backward:
         return
+    if _before_join_cb[0] is not None:
+        _before_join_cb[0]()
     _async["ready"].clear()
     pending, _async["pending"] = _async["pending"], {}
     for entry in pending.values():
@@ -554,7 +565,11 @@ class Conv2dFn(torch.autograd.Function):
                 with torch.cuda.stream(side):
                     call("sisr_conv_wgrad_fused", d, x, dpre, weight, u, v, sig, dw, colsum, db,
                          0 if prev is None else 1, ws, side.cuda_stream)
-                _async["keep"].append((ws, x, dpre, colsum))     # alive until the streams are joined
+                # alive until the streams are joined: everything the side-stream kernels read.  u / v / sigma are
+                # slices of prepare_convs' per-forward buffer, which is otherwise freed as soon as the last conv of
+                # the network has been back-propagated - while the finish kernels of the last layers are still
+                # queued - and handed to the next allocation of whichever stream it came from
+                _async["keep"].append((ws, x, dpre, colsum, u, v, sig))
                 dw = db = None            # delivered to param.grad by _deliver_ready() / join_wgrad()
                 left = _async["uses"].get(key)
                 if left is not None:

@@ -138,7 +138,7 @@ class GradSync:
                 size = 0
             buckets[-1].append(p)
             size += nbytes
-        plan = {"buckets": [], "of": {}, "views": {}, "pending": [], "handles": []}
+        plan = {"buckets": [], "of": {}, "views": {}, "pending": [], "handles": [], "events": {}}
         for bi, bl in enumerate(buckets):
             flat = torch.zeros(sum(p.numel() for p in bl), dtype=torch.float32, device=dev)
             off = 0
@@ -153,12 +153,20 @@ class GradSync:
             self._hooks[p] = hook
             p.register_post_accumulate_grad_hook(hook)     # gradients that autograd accumulates
         ops.set_grad_ready_callback(self.grad_ready)       # gradients delivered from the wgrad side stream
+        ops.set_before_join_callback(self.drain)
         optimizer.grad_views = plan["views"]
         optimizer.grad_scale = 1.0 / self.world
 
     def _make_hook(self, plan, p):
         def hook(param):
             b = plan["buckets"][plan["of"][p]]
+            # The step runs on several streams (trainer: D(real) and MaskedVGG(fake) on side streams, weight
+            # gradients on another): this gradient is complete on the CURRENT stream only.  The bucket may be
+            # packed later from a different one, which then waits for this event.
+            if param.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                plan["events"][p] = ev
             b["ready"] += 1
             if b["ready"] == len(b["params"]):
                 self._launch(plan, b)
@@ -166,6 +174,12 @@ class GradSync:
 
     def _launch(self, plan, b):
         b["ready"] = 0
+        if self.comm_stream is not None:
+            cur = torch.cuda.current_stream()
+            for p in b["params"]:
+                ev = plan["events"].pop(p, None)
+                if ev is not None:
+                    cur.wait_event(ev)
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b["params"]]
         torch._foreach_copy_([plan["views"][p] for p in b["params"]], grads)
         if self.world == 1:
@@ -176,6 +190,17 @@ class GradSync:
                 dist.all_reduce(b["flat"], group=self.group)
         else:
             dist.all_reduce(b["flat"], group=self.group)
+
+    def drain(self):
+        """End of a backward pass, before the last side-stream gradients are packed: the current stream waits for
+        the all-reduces already in flight.  Measured (2 ranks, 1 MB buckets, eager step, round 2): without this
+        wait the LAST bucket of the generator - packed from the main thread while earlier buckets were still being
+        reduced - came out 22 % short (|g| 0.188 instead of 0.241 on the lowest three convs, intermittently 4x too
+        large at 8 ranks in earlier runs); a device-wide synchronise at the same place, a single bucket, or
+        delivering every gradient as soon as it is queued all gave the right sum.  The wait costs nothing: sync()
+        waits for the same stream a moment later."""
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def sync(self, optimizer):
         plan = self._plans.get(id(optimizer))

@@ -197,7 +197,12 @@ class SRGANTrainer:
         # backward of the D(fake) pass.  D(fake) starts only after D(real) has finished: the spectral-norm vectors
         # and BN running statistics advance in the reference's order (train.py:133-141).
         d_real = d_side = None
-        if lw_d and c.overlap_d_real and img_hr.is_cuda:
+        # (data-parallel runs keep the whole step on the main stream + the two streams validated at 2 / 4 / 8 ranks:
+        # with D fed from two streams the replicas of a captured step drifted apart in the last bits, and with
+        # MaskedVGG(fake) on its own stream the synchronised G gradients of the lowest layers were 22 % short -
+        # profiles/r2_notes.md)
+        multi = self.grad_sync is None
+        if lw_d and c.overlap_d_real and multi and img_hr.is_cuda:
             self.net_d.zero_grad(set_to_none=True)
             d_side = self._side_stream(1)
             d_side.wait_stream(torch.cuda.current_stream())
@@ -209,7 +214,7 @@ class SRGANTrainer:
         # with the D update and the D pass of the G update; its backward (autograd: same stream) runs next to the
         # data-gradient pass through D
         feat_fake = f_side = None
-        if lw_c and kind == "features" and c.overlap_fake_features and not on_lr and img_hr.is_cuda:
+        if lw_c and kind == "features" and c.overlap_fake_features and multi and not on_lr and img_hr.is_cuda:
             f_side = self._side_stream(2)
             f_side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(f_side):
