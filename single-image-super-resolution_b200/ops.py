@@ -213,10 +213,13 @@ def join_wgrad(end_of_backward: bool = True):
     _async["keep"].clear()
     if not end_of_backward:
         return
-    if _before_join_cb[0] is not None:
-        _before_join_cb[0]()
+
     _async["ready"].clear()
     pending, _async["pending"] = _async["pending"], {}
+    # (only with gradients to hand over: begin_step() calls this too, possibly as the first thing of a CUDA-graph
+    # capture, where a wait on the uncaptured all-reduces of the preceding eager steps would be illegal)
+    if pending and _before_join_cb[0] is not None:
+        _before_join_cb[0]()
     for entry in pending.values():
         _deliver(entry)
 

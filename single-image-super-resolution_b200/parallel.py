@@ -107,6 +107,7 @@ class GradSync:
         self._plans: Dict[int, dict] = {}
         self._hooks: Dict[torch.nn.Parameter, object] = {}
         self.comm_stream = None
+        self._in_flight = False         # an all-reduce has been launched since the last sync()
 
     def grad_ready(self, param):
         """Public entry for gradients that bypass autograd's accumulation (ops.set_grad_ready_callback)."""
@@ -184,6 +185,7 @@ class GradSync:
         torch._foreach_copy_([plan["views"][p] for p in b["params"]], grads)
         if self.world == 1:
             return
+        self._in_flight = True
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
@@ -199,7 +201,9 @@ class GradSync:
         large at 8 ranks in earlier runs); a device-wide synchronise at the same place, a single bucket, or
         delivering every gradient as soon as it is queued all gave the right sum.  The wait costs nothing: sync()
         waits for the same stream a moment later."""
-        if self.comm_stream is not None:
+        if self.comm_stream is not None and self._in_flight:
+            # (only all-reduces launched since the last sync(): a wait on older work would be a dependency on
+            # uncaptured work when the step is being captured into a CUDA graph)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def sync(self, optimizer):
@@ -211,3 +215,4 @@ class GradSync:
                 self._launch(plan, b)
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._in_flight = False

@@ -214,7 +214,7 @@ class SRGANTrainer:
         # with the D update and the D pass of the G update; its backward (autograd: same stream) runs next to the
         # data-gradient pass through D
         feat_fake = f_side = None
-        if lw_c and kind == "features" and c.overlap_fake_features and multi and not on_lr and img_hr.is_cuda:
+        if lw_c and kind == "features" and c.overlap_fake_features and not on_lr and img_hr.is_cuda:
             f_side = self._side_stream(2)
             f_side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(f_side):
