@@ -197,12 +197,11 @@ class SRGANTrainer:
         # backward of the D(fake) pass.  D(fake) starts only after D(real) has finished: the spectral-norm vectors
         # and BN running statistics advance in the reference's order (train.py:133-141).
         d_real = d_side = None
-        # (data-parallel runs keep the whole step on the main stream + the two streams validated at 2 / 4 / 8 ranks:
-        # with D fed from two streams the replicas of a captured step drifted apart in the last bits, and with
-        # MaskedVGG(fake) on its own stream the synchronised G gradients of the lowest layers were 22 % short -
-        # profiles/r2_notes.md)
-        multi = self.grad_sync is None
-        if lw_d and c.overlap_d_real and multi and img_hr.is_cuda:
+        # (not in data-parallel runs: with D's parameters fed from two streams the replicas of a CAPTURED step drifted
+        # apart in the last bits - bench dp_check `weights_identical: false` at 2 ranks - although the eager step
+        # passed tools/multi_gpu_check.py; cause not found within the round's GPU budget, profiles/r2_notes.md)
+        single = self.grad_sync is None
+        if lw_d and c.overlap_d_real and single and img_hr.is_cuda:
             self.net_d.zero_grad(set_to_none=True)
             d_side = self._side_stream(1)
             d_side.wait_stream(torch.cuda.current_stream())
