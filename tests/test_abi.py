@@ -118,8 +118,14 @@ def test_bench_configs_and_traffic_source():
     assert abs(b.CONFIGS["x4"]["flop"] - 42.55e9) < 1e6 and abs(b.CONFIGS["frozen"]["flop"] - 38.66e9) < 1e6
     assert abs(b.CONFIGS["x8"]["flop"] - 280.75e9) < 1e6 and b.CONFIGS["x8"]["hr"] == 256
     t = b.ncu_traffic()
-    assert t["source"] and t["source"].startswith("profiles/") and t["bytes"] > 1e6
-    assert os.path.exists(os.path.join(ROOT, t["source"]))
+    # either a committed capture of the kernel the trunk runs NOW (igemm_pm_kernel) or null - never a number measured
+    # on a kernel that is no longer on the path
+    if t["source"] is None:
+        assert t["bytes"] is None
+    else:
+        assert t["source"].startswith("profiles/") and t["bytes"] > 1e6
+        assert os.path.exists(os.path.join(ROOT, t["source"]))
+        assert "igemm_pm_kernel" in open(os.path.join(ROOT, t["source"])).read()
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert '"traffic": 4831488' not in src
     assert "reference_train_loop_time" in src and 'kind": "reference"' in src.replace("'", '"')
