@@ -66,6 +66,19 @@ def _worker(rank, world, port, ret):
         ok = ok and ops._world() == world
     # gradients that bypass autograd reach the buckets through the public callback
     ok = ok and ops._grad_ready_cb[0] is not None and ops._grad_ready_cb[0].__self__ is sync
+    # end-of-backward hook: GradSync.drain is registered, only runs when side-stream gradients are handed over
+    # (begin_step() calls join_wgrad() too - as the first thing of a CUDA-graph capture), and only waits for
+    # all-reduces launched since the last sync()
+    ok = ok and ops._before_join_cb[0] is not None and ops._before_join_cb[0].__self__ is sync
+    ok = ok and sync._in_flight is False
+    calls = []
+    ops.set_before_join_callback(lambda: calls.append(1))
+    ops.join_wgrad()
+    ok = ok and calls == []
+    ops._async["pending"]["k"] = (None, None, None, None, False, False)
+    ops.join_wgrad()
+    ok = ok and calls == [1] and not ops._async["pending"]
+    ops.set_before_join_callback(sync.drain)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
